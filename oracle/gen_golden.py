@@ -1,0 +1,54 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/ref_harness_g*).
+
+Run in the build container (needs /root/reference for `make -C oracle ref`):
+    python oracle/gen_golden.py
+Each fixture stores, per cycle and per emulated rank, the reference's per-cell arrays and scalars in
+full and the first PHOTON_LIMIT photons' pre/post transport records, as raw IEEE doubles / integers.
+TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from branson_b200 import decks  # noqa: E402
+from oracle import refio  # noqa: E402
+
+PHOTON_LIMIT = 1000
+
+
+def golden_cases():
+    """name -> (deck, n_ranks).  Also imported by the tests so both sides build identical decks."""
+    return {
+        "three_region_g1_r1": (decks.simple_three_region(photons=3000, n_groups=1), 1),
+        "three_region_g30_r2": (decks.simple_three_region(photons=3000, n_groups=30), 2),
+        "marshak_r1": (decks.marshak_wave(photons=3000, t_stop=0.04), 1),
+        "hot_zone_s10_r1": (decks.hot_zone(photons=5000, t_stop=0.03, scale=10), 1),
+        "hohlraum_s5_g30_r1": (decks.hohlraum_single(photons=20000, t_stop=0.02, scale=5), 1),
+        "hohlraum_multi_s10_g30_r4": (decks.hohlraum_multi(photons=8000, t_stop=0.003, scale=10), 4),
+    }
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (deck, n_ranks) in golden_cases().items():
+        dumps, _ = refio.run_reference(deck, n_ranks=n_ranks, photon_limit=PHOTON_LIMIT)
+        flat = {}
+        for r, d in enumerate(dumps):
+            for k, v in d.items():
+                if k.endswith("transport_seconds"):
+                    continue
+                flat[f"r{r}/{k}"] = v
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **flat)
+        print(f"{name}: {len(flat)} arrays, {os.path.getsize(path) / 1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    main()
