@@ -1,0 +1,952 @@
+// branson_gpu.cu -- context + C ABI (include/branson_gpu.h) of the B200 IMC hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see csrc/Makefile).  -fmad=false keeps the
+// reference-stated arithmetic un-contracted, like the reference's own CPU build (src/CMakeLists.txt:93 has no -march,
+// so gcc emits no FMA): pos += angle*d, (1-f)*sigma_a + sigma_s, ... round exactly as on the host.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/branson_gpu.h"
+#include "census.cuh"
+#include "common.cuh"
+#include "event.cuh"
+#include "source.cuh"
+#include "transport.cuh"
+
+using namespace bg;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct bgpu_ctx {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  std::string err;
+
+  MeshDev mesh{};
+  double *d_faces = nullptr;
+  uint32_t seed = 0;
+  uint64_t n_user = 0;
+  int rank = 0, n_ranks = 1;
+  uint64_t ctr_hi = 0;
+
+  // cell data
+  double *d_f = nullptr, *d_opa = nullptr, *d_ops = nullptr;  // f [n_cells]; opa/ops [n_cells*G]
+  double *d_cell_stage = nullptr;                               // 3*n_cells staging (gray values / E arrays)
+  bool have_cell_data = false;
+
+  // photons
+  PhotonSoA work{}, census{};
+  uint64_t n_work = 0, n_new = 0, n_census = 0;
+  uint8_t *d_desc = nullptr;
+  uint64_t desc_cap = 0;
+  uint32_t *d_counters = nullptr;
+  uint64_t counters_cap = 0;
+  bool counters_on = false;
+
+  // tallies: interleaved {abs_E, track_E}[n_cells] + extra doubles for the packed all-reduce
+  double *d_tally = nullptr;
+  uint64_t tally_extra = 0;
+
+  unsigned long long *d_stats = nullptr;  // ST_COUNT counters
+  unsigned long long *d_work_counter = nullptr;
+  double *d_results = nullptr;  // [0] census_E [1] exit_E
+
+  // scratch (grown on demand)
+  DevBuf scr_counts, scr_offsets, scr_tile_sum, scr_tile_off, scr_tiles, scr_ndep, scr_dep_off, scr_dep_cell,
+      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event;
+  void *h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+
+  // launch config
+  int block_threads = 128;
+  int blocks_per_sm = 0;  // 0: occupancy query
+  uint32_t chunk = 128;
+
+  bgpu_cycle_stats stats{};
+  double pre_census_E = 0.0;
+  bool stats_valid = false;
+};
+
+namespace {
+
+int fail(bgpu_ctx *c, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return 1;
+}
+
+#define CU(c, call)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail((c), "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, #call); \
+  } while (0)
+
+int ensure(bgpu_ctx *c, DevBuf &b, size_t bytes) {
+  if (bytes <= b.bytes) return 0;
+  if (b.p) CU(c, cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CU(c, cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return 0;
+}
+
+int ensure_pinned(bgpu_ctx *c, size_t bytes) {
+  if (bytes <= c->h_pinned_bytes) return 0;
+  if (c->h_pinned) CU(c, cudaFreeHost(c->h_pinned));
+  c->h_pinned = nullptr;
+  c->h_pinned_bytes = 0;
+  CU(c, cudaHostAlloc(&c->h_pinned, bytes + bytes / 8 + 256, cudaHostAllocDefault));
+  c->h_pinned_bytes = bytes + bytes / 8 + 256;
+  return 0;
+}
+
+void carve(PhotonSoA &s, void *base, uint64_t cap) {
+  char *p = (char *)base;
+  s.base = base;
+  s.cap = cap;
+  s.xy = (double2 *)p;                 p += 16 * cap;
+  s.za = (double2 *)p;                 p += 16 * cap;
+  s.bc = (double2 *)p;                 p += 16 * cap;
+  s.ee = (double2 *)p;                 p += 16 * cap;
+  s.lc = (ulonglong2 *)p;              p += 16 * cap;
+  s.sg = (ulonglong2 *)p;
+}
+
+// grow a photon list to hold at least n photons, keeping the first `keep` photons
+int ensure_soa(bgpu_ctx *c, PhotonSoA &s, uint64_t n, uint64_t keep) {
+  if (n <= s.cap) return 0;
+  uint64_t cap = std::max<uint64_t>(n + n / 4, 1024);
+  cap = (cap + 15) & ~15ull;
+  void *base = nullptr;
+  CU(c, cudaMalloc(&base, 96 * cap));
+  PhotonSoA t{};
+  carve(t, base, cap);
+  if (keep && s.base) {
+    CU(c, cudaMemcpyAsync(t.xy, s.xy, 16 * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(t.za, s.za, 16 * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(t.bc, s.bc, 16 * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(t.ee, s.ee, 16 * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(t.lc, s.lc, 16 * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(t.sg, s.sg, 16 * keep, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  if (s.base) CU(c, cudaFree(s.base));
+  s = t;
+  return 0;
+}
+
+int ensure_work(bgpu_ctx *c, uint64_t n, uint64_t keep) {
+  if (ensure_soa(c, c->work, n, keep)) return 1;
+  if (c->desc_cap < c->work.cap) {
+    if (c->d_desc) CU(c, cudaFree(c->d_desc));
+    c->d_desc = nullptr;
+    CU(c, cudaMalloc((void **)&c->d_desc, c->work.cap + 64));
+    c->desc_cap = c->work.cap;
+  }
+  if (c->counters_on && c->counters_cap < c->work.cap) {
+    if (c->d_counters) CU(c, cudaFree(c->d_counters));
+    c->d_counters = nullptr;
+    CU(c, cudaMalloc((void **)&c->d_counters, 16 * c->work.cap));
+    c->counters_cap = c->work.cap;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_expand_groups(uint32_t n_cells, uint32_t G, const double *__restrict__ a,
+                                const double *__restrict__ s, double *__restrict__ opa, double *__restrict__ ops) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)n_cells * G) return;
+  const uint32_t cell = (uint32_t)(t / G);
+  opa[t] = a[cell];
+  ops[t] = s[cell];
+}
+
+__global__ void k_copy_soa(PhotonSoA src, uint64_t src_off, PhotonSoA dst, uint64_t dst_off, uint64_t n) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  dst.xy[dst_off + t] = src.xy[src_off + t];
+  dst.za[dst_off + t] = src.za[src_off + t];
+  dst.bc[dst_off + t] = src.bc[src_off + t];
+  dst.ee[dst_off + t] = src.ee[src_off + t];
+  dst.lc[dst_off + t] = src.lc[src_off + t];
+  dst.sg[dst_off + t] = src.sg[src_off + t];
+}
+
+// in-order (tile-tree) sum of E over a photon list: get_photon_list_E (src/census_functions.h:31-46)
+__global__ void __launch_bounds__(CT_THREADS) k_list_E_tiles(const double2 *__restrict__ ee, uint64_t n,
+                                                             double *__restrict__ tile_E) {
+  __shared__ double s_red[CT_THREADS >> 5];
+  const uint64_t base = (uint64_t)blockIdx.x * CT_TILE + (uint64_t)threadIdx.x * CT_ITEMS;
+  double e = 0.0;
+#pragma unroll
+  for (int i = 0; i < CT_ITEMS; ++i)
+    if (base + i < n) e += ee[base + i].x;
+  const double b = block_sum(e, s_red);
+  if (threadIdx.x == 0) tile_E[blockIdx.x] = b;
+}
+__global__ void k_sum_serial(const double *__restrict__ v, uint32_t n, double *out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (uint32_t i = 0; i < n; ++i) s += v[i];
+    *out = s;
+  }
+}
+
+// reference AoS Photon (120 bytes, src/photon.h:171-182) <-> device SoA
+__global__ void k_aos_to_soa(const uint64_t *__restrict__ aos, uint64_t n, PhotonSoA ph, uint64_t ctr_hi,
+                             unsigned long long *stats) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint64_t *w = aos + 15 * t;
+  const uint64_t w0 = w[0];
+  ph.xy[t] = make_double2(__longlong_as_double(w[2]), __longlong_as_double(w[3]));
+  ph.za[t] = make_double2(__longlong_as_double(w[4]), __longlong_as_double(w[5]));
+  ph.bc[t] = make_double2(__longlong_as_double(w[6]), __longlong_as_double(w[7]));
+  ph.ee[t] = make_double2(__longlong_as_double(w[8]), __longlong_as_double(w[9]));
+  ph.lc[t] = make_ulonglong2(w[10], w[11]);
+  ph.sg[t] = make_ulonglong2(w[13], w0);  // cell | group << 32 is exactly word 0
+  if (w[12] != ctr_hi || w[14] != 0ull) atomicAdd(&stats[ST_BAD_RNG], 1ull);
+}
+__global__ void k_soa_to_aos(uint64_t *__restrict__ aos, uint64_t n, PhotonSoA ph, const uint8_t *__restrict__ desc) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint64_t *w = aos + 15 * t;
+  const double2 xy = ph.xy[t], za = ph.za[t], bc = ph.bc[t], ee = ph.ee[t];
+  const ulonglong2 lc = ph.lc[t], sg = ph.sg[t];
+  w[0] = sg.y;
+  // descriptors[0] = event (Photon::set_descriptor, src/photon.h); keep source_type and the padding bytes
+  w[1] = (w[1] & 0xffffff00ffffffffull) | ((uint64_t)desc[t] << 32);
+  w[2] = __double_as_longlong(xy.x); w[3] = __double_as_longlong(xy.y); w[4] = __double_as_longlong(za.x);
+  w[5] = __double_as_longlong(za.y); w[6] = __double_as_longlong(bc.x); w[7] = __double_as_longlong(bc.y);
+  w[8] = __double_as_longlong(ee.x);
+  w[10] = lc.x;
+  w[11] = lc.y;
+}
+
+// deterministic tally: segment bounds of the cell-sorted deposit log, then in-order sums
+__global__ void k_seg_bounds(const uint32_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ seg_start,
+                             uint64_t *__restrict__ seg_end) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t k = keys[t];
+  if (t == 0 || keys[t - 1] != k) seg_start[k] = t;
+  if (t == n - 1 || keys[t + 1] != k) seg_end[k] = t + 1;
+}
+__global__ void k_seg_sum(uint32_t n_cells, const uint64_t *__restrict__ seg_start,
+                          const uint64_t *__restrict__ seg_end, const uint32_t *__restrict__ order,
+                          const double2 *__restrict__ dep_val, double2 *__restrict__ tally) {
+  const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const uint64_t b = seg_start[cell], e = seg_end[cell];
+  if (e <= b) return;
+  double2 acc = tally[cell];
+  for (uint64_t p = b; p < e; ++p) {
+    const double2 v = dep_val[order[p]];
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  tally[cell] = acc;
+}
+__global__ void k_iota(uint32_t *v, uint64_t n) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) v[t] = (uint32_t)t;
+}
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// exclusive scan of n u32 -> n+1 u64 on the ctx stream
+int device_scan(bgpu_ctx *c, const uint32_t *in, uint64_t n, uint64_t *out) {
+  if (n == 0) {
+    CU(c, cudaMemsetAsync(out, 0, 8, c->stream));
+    return 0;
+  }
+  const uint32_t tiles = (uint32_t)((n + CT_TILE - 1) / CT_TILE);
+  if (ensure(c, c->scr_tile_sum, 4ull * tiles)) return 1;
+  if (ensure(c, c->scr_tile_off, 8ull * (tiles + 1))) return 1;
+  k_scan_tile_sums<<<tiles, CT_THREADS, 0, c->stream>>>(in, n, (uint32_t *)c->scr_tile_sum.p);
+  k_scan_single<<<1, 1024, 0, c->stream>>>((const uint32_t *)c->scr_tile_sum.p, tiles, (uint64_t *)c->scr_tile_off.p);
+  k_scan_apply<<<tiles, CT_THREADS, 0, c->stream>>>(in, n, (const uint64_t *)c->scr_tile_off.p, out);
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+template <int MODE>
+int launch_history(bgpu_ctx *c, const TransportParams &P) {
+  const size_t smem = (size_t)P.mesh.n_faces * 8;
+  const bool use_smem = smem <= 160 * 1024;
+  const bool ctrs = P.counters != nullptr;
+  void (*kern)(const TransportParams) = nullptr;
+  if (use_smem) kern = ctrs ? k_transport_history<MODE, true, true> : k_transport_history<MODE, false, true>;
+  else kern = ctrs ? k_transport_history<MODE, true, false> : k_transport_history<MODE, false, false>;
+  if (use_smem && smem > 48 * 1024)
+    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = c->blocks_per_sm;
+  if (per_sm <= 0) {
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, c->block_threads, use_smem ? smem : 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  uint64_t blocks = (uint64_t)c->n_sm * per_sm;
+  const uint64_t max_useful = (P.n + c->block_threads - 1) / c->block_threads;
+  if (blocks > max_useful) blocks = std::max<uint64_t>(max_useful, 1);
+  kern<<<(unsigned)blocks, c->block_threads, use_smem ? smem : 0, c->stream>>>(P);
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
+  TransportParams P{};
+  P.ph = c->work;
+  P.n = c->n_work;
+  P.desc = c->d_desc;
+  P.counters = c->counters_on ? c->d_counters : nullptr;
+  P.mesh = c->mesh;
+  P.f = c->d_f;
+  P.opa = c->d_opa;
+  P.ops = c->d_ops;
+  P.tally = (double2 *)c->d_tally;
+  P.ctr_hi = c->ctr_hi;
+  P.work_counter = c->d_work_counter;
+  P.chunk = c->chunk;
+  P.writeback_all = writeback_all ? 1 : 0;
+  P.stats = c->d_stats;
+  return P;
+}
+
+// the history loop over the device work list; tallies are ACCUMULATED into d_tally
+int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all) {
+  if (!c->have_cell_data) return fail(c, "bgpu_transport: cell data not set (call bgpu_set_cell_data first)");
+  if (algorithm != BGPU_HISTORY && algorithm != BGPU_EVENT) return fail(c, "unknown transport algorithm %d", algorithm);
+  if (tally_mode != BGPU_TALLY_ATOMIC && tally_mode != BGPU_TALLY_DETERMINISTIC)
+    return fail(c, "unknown tally mode %d", tally_mode);
+  CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
+  if (c->n_work == 0) return 0;
+  TransportParams P = make_params(c, writeback_all);
+  if (algorithm == BGPU_EVENT) {
+    if (tally_mode != BGPU_TALLY_ATOMIC) return fail(c, "the event-based variant supports BGPU_TALLY_ATOMIC only");
+    return run_event_transport(c->stream, P, c->n_sm, c->scr_event.p, c->scr_event.bytes,
+                               [&](size_t bytes) { return ensure(c, c->scr_event, bytes) ? (void *)nullptr : c->scr_event.p; },
+                               c->err);
+  }
+  if (tally_mode == BGPU_TALLY_ATOMIC) {
+    CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
+    return launch_history<TM_ATOMIC>(c, P);
+  }
+  // ---- deterministic: count deposits, scan, log, stable sort by cell, in-order segment sums ----
+  const uint64_t n = c->n_work;
+  if (ensure(c, c->scr_ndep, 4 * n)) return 1;
+  if (ensure(c, c->scr_dep_off, 8 * (n + 1))) return 1;
+  P.ndep = (uint32_t *)c->scr_ndep.p;
+  CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
+  if (launch_history<TM_COUNT>(c, P)) return 1;
+  if (device_scan(c, P.ndep, n, (uint64_t *)c->scr_dep_off.p)) return 1;
+  uint64_t n_dep = 0;
+  CU(c, cudaMemcpyAsync(&n_dep, (uint64_t *)c->scr_dep_off.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (n_dep >= (1ull << 32)) return fail(c, "deterministic tally mode: %llu deposits exceed 2^32", (unsigned long long)n_dep);
+  if (ensure(c, c->scr_dep_cell, 4 * n_dep)) return 1;
+  if (ensure(c, c->scr_dep_val, 16 * n_dep)) return 1;
+  P.dep_off = (const uint64_t *)c->scr_dep_off.p;
+  P.dep_cell = (uint32_t *)c->scr_dep_cell.p;
+  P.dep_val = (double2 *)c->scr_dep_val.p;
+  CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
+  CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
+  if (launch_history<TM_LOG>(c, P)) return 1;
+  if (n_dep == 0) return 0;
+  if (ensure(c, c->scr_keys_out, 4 * n_dep)) return 1;
+  if (ensure(c, c->scr_vals_in, 4 * n_dep)) return 1;
+  if (ensure(c, c->scr_vals_out, 4 * n_dep)) return 1;
+  k_iota<<<grid_for(n_dep, 256), 256, 0, c->stream>>>((uint32_t *)c->scr_vals_in.p, n_dep);
+  int end_bit = 1;
+  while ((1ull << end_bit) < c->mesh.n_cells) ++end_bit;
+  size_t tmp_bytes = 0;
+  CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)c->scr_dep_cell.p,
+                                        (uint32_t *)c->scr_keys_out.p, (const uint32_t *)c->scr_vals_in.p,
+                                        (uint32_t *)c->scr_vals_out.p, (int)n_dep, 0, end_bit, c->stream));
+  if (ensure(c, c->scr_sort, tmp_bytes)) return 1;
+  CU(c, cub::DeviceRadixSort::SortPairs(c->scr_sort.p, tmp_bytes, (const uint32_t *)c->scr_dep_cell.p,
+                                        (uint32_t *)c->scr_keys_out.p, (const uint32_t *)c->scr_vals_in.p,
+                                        (uint32_t *)c->scr_vals_out.p, (int)n_dep, 0, end_bit, c->stream));
+  if (ensure(c, c->scr_seg, 16ull * c->mesh.n_cells)) return 1;
+  CU(c, cudaMemsetAsync(c->scr_seg.p, 0, 16ull * c->mesh.n_cells, c->stream));
+  uint64_t *seg_start = (uint64_t *)c->scr_seg.p, *seg_end = seg_start + c->mesh.n_cells;
+  k_seg_bounds<<<grid_for(n_dep, 256), 256, 0, c->stream>>>((const uint32_t *)c->scr_keys_out.p, n_dep, seg_start,
+                                                             seg_end);
+  k_seg_sum<<<grid_for(c->mesh.n_cells, 128), 128, 0, c->stream>>>(c->mesh.n_cells, seg_start, seg_end,
+                                                                   (const uint32_t *)c->scr_vals_out.p,
+                                                                   (const double2 *)c->scr_dep_val.p,
+                                                                   (double2 *)c->d_tally);
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+// post_process_photons: compaction of CENSUS photons of the work list into the census list
+int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
+  const uint64_t n = c->n_work;
+  c->n_census = 0;
+  double res[2] = {0.0, 0.0};
+  unsigned long long st[ST_COUNT] = {};
+  if (n) {
+    const uint32_t tiles = (uint32_t)((n + CT_TILE - 1) / CT_TILE);
+    const size_t per = 4ull * 3 + 8ull * 2;
+    if (ensure(c, c->scr_tiles, per * tiles + 8ull * (tiles + 1) + 64)) return 1;
+    TilePartials T;
+    char *p = (char *)c->scr_tiles.p;
+    T.census_E = (double *)p;    p += 8ull * tiles;
+    T.exit_E = (double *)p;      p += 8ull * tiles;
+    T.tile_off = (uint64_t *)p;  p += 8ull * (tiles + 1);
+    T.n_census = (uint32_t *)p;  p += 4ull * tiles;
+    T.n_killed = (uint32_t *)p;  p += 4ull * tiles;
+    T.n_exit = (uint32_t *)p;
+    k_census_tiles<<<tiles, CT_THREADS, 0, c->stream>>>(c->d_desc, c->work.ee, n, T);
+    k_scan_partials<<<1, 1024, 0, c->stream>>>(tiles, T, c->d_results, c->d_stats);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(st, c->d_stats, 8 * ST_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(res, c->d_results, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const uint64_t nc = st[ST_N_CENSUS];
+    if (ensure_soa(c, c->census, nc, 0)) return 1;
+    if (nc) {
+      k_census_scatter<<<tiles, CT_THREADS, 0, c->stream>>>(c->d_desc, c->work, n, c->census, 0, T.tile_off,
+                                                            K_C * next_dt);
+      CU(c, cudaGetLastError());
+    }
+    c->n_census = nc;
+    if (serial_sums) {
+      // the reference's strictly serial photon-order sums (src/post_process_functions.h:41-55), on the host
+      if (ensure_pinned(c, 17 * n)) return 1;
+      double2 *h_ee = (double2 *)c->h_pinned;
+      uint8_t *h_d = (uint8_t *)c->h_pinned + 16 * n;
+      CU(c, cudaMemcpyAsync(h_ee, c->work.ee, 16 * n, cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaMemcpyAsync(h_d, c->d_desc, n, cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      double ce = 0.0, xe = 0.0;
+      for (uint64_t i = 0; i < n; ++i) {
+        if (h_d[i] == EV_CENSUS) ce += h_ee[i].x;
+        else if (h_d[i] == EV_EXIT) xe += h_ee[i].x;
+      }
+      res[0] = ce;
+      res[1] = xe;
+    }
+  }
+  bgpu_cycle_stats &s = c->stats;
+  s.census_E = res[0];
+  s.exit_E = res[1];
+  s.n_census = c->n_census;
+  s.n_killed = st[ST_N_KILLED];
+  s.n_exit = st[ST_N_EXIT];
+  s.n_events = st[ST_EVENTS];
+  s.n_scatters = st[ST_SCATTERS];
+  s.n_crossings = st[ST_CROSSINGS];
+  s.n_reflections = st[ST_REFLECTIONS];
+  s.n_deposits = st[ST_DEPOSITS];
+  s.n_group_lookups = st[ST_LOOKUPS];
+  return 0;
+}
+
+int list_energy(bgpu_ctx *c, const PhotonSoA &list, uint64_t off, uint64_t n, double *out) {
+  *out = 0.0;
+  if (!n) return 0;
+  const uint32_t tiles = (uint32_t)((n + CT_TILE - 1) / CT_TILE);
+  if (ensure(c, c->scr_tile_sum, 8ull * tiles + 8)) return 1;
+  double *tile_E = (double *)c->scr_tile_sum.p;
+  k_list_E_tiles<<<tiles, CT_THREADS, 0, c->stream>>>(list.ee + off, n, tile_E);
+  k_sum_serial<<<1, 32, 0, c->stream>>>(tile_E, tiles, c->d_results + 2);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(out, c->d_results + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" {
+
+int bgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char *bgpu_last_error(const bgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
+  if (!out || !d) return fail(nullptr, "bgpu_create: null argument");
+  *out = nullptr;
+  if (d->abi_version != BGPU_ABI_VERSION) return fail(nullptr, "bgpu_create: ABI version %u != %u", d->abi_version, BGPU_ABI_VERSION);
+  if (!d->nx || !d->ny || !d->nz || !d->n_groups || !d->x_faces || !d->y_faces || !d->z_faces)
+    return fail(nullptr, "bgpu_create: empty mesh description");
+  if ((uint64_t)d->nx * d->ny * d->nz >= (1ull << 32)) return fail(nullptr, "bgpu_create: more than 2^32 cells");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, "bgpu_create: no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+  bgpu_ctx *c = new bgpu_ctx();
+  // rank -> device map of the reference (src/gpu_setup.h:68-78)
+  int dev = d->device;
+  if (dev < 0) dev = (d->n_ranks <= n_dev) ? d->rank : d->rank % n_dev;
+  if (dev >= n_dev) dev = dev % n_dev;
+  c->device = dev;
+#define CUC(call)                                                                                              \
+  do {                                                                                                         \
+    cudaError_t e__ = (call);                                                                                  \
+    if (e__ != cudaSuccess) {                                                                                  \
+      fail(nullptr, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, #call);           \
+      delete c;                                                                                                \
+      return 1;                                                                                                \
+    }                                                                                                          \
+  } while (0)
+  CUC(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, dev));
+  c->n_sm = prop.multiProcessorCount;
+  CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev) CUC(cudaEventCreate(&ev));
+  c->mesh.nx = d->nx; c->mesh.ny = d->ny; c->mesh.nz = d->nz; c->mesh.G = d->n_groups;
+  c->mesh.n_cells = d->nx * d->ny * d->nz;
+  c->mesh.n_faces = d->nx + d->ny + d->nz + 3;
+  for (int i = 0; i < 6; ++i) c->mesh.bc[i] = d->bc[i];
+  c->seed = d->seed;
+  c->ctr_hi = ((uint64_t)d->seed) << 32;
+  c->n_user = d->n_user_photons;
+  c->rank = d->rank;
+  c->n_ranks = d->n_ranks < 1 ? 1 : d->n_ranks;
+  std::vector<double> faces;
+  faces.insert(faces.end(), d->x_faces, d->x_faces + d->nx + 1);
+  faces.insert(faces.end(), d->y_faces, d->y_faces + d->ny + 1);
+  faces.insert(faces.end(), d->z_faces, d->z_faces + d->nz + 1);
+  CUC(cudaMalloc((void **)&c->d_faces, 8 * faces.size()));
+  CUC(cudaMemcpy(c->d_faces, faces.data(), 8 * faces.size(), cudaMemcpyHostToDevice));
+  c->mesh.faces = c->d_faces;
+  const uint64_t nc = c->mesh.n_cells, G = c->mesh.G;
+  CUC(cudaMalloc((void **)&c->d_f, 8 * nc));
+  CUC(cudaMalloc((void **)&c->d_opa, 8 * nc * G));
+  CUC(cudaMalloc((void **)&c->d_ops, 8 * nc * G));
+  CUC(cudaMalloc((void **)&c->d_cell_stage, 8 * nc * 3));
+  CUC(cudaMalloc((void **)&c->d_tally, 16 * nc));
+  CUC(cudaMemset(c->d_tally, 0, 16 * nc));
+  CUC(cudaMalloc((void **)&c->d_stats, 8 * ST_COUNT));
+  CUC(cudaMemset(c->d_stats, 0, 8 * ST_COUNT));
+  CUC(cudaMalloc((void **)&c->d_work_counter, 8));
+  CUC(cudaMalloc((void **)&c->d_results, 8 * 8));
+  uint64_t cap = d->photon_capacity;
+  if (!cap) cap = (uint64_t)(1.25 * (double)d->n_user_photons / (double)c->n_ranks) + 1024;
+  if (ensure_work(c, cap, 0)) {
+    g_create_error = c->err;
+    delete c;
+    return 1;
+  }
+#undef CUC
+  *out = c;
+  return 0;
+}
+
+void bgpu_destroy(bgpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->scr_counts, &c->scr_offsets, &c->scr_tile_sum, &c->scr_tile_off, &c->scr_tiles, &c->scr_ndep,
+                    &c->scr_dep_off, &c->scr_dep_cell, &c->scr_dep_val, &c->scr_sort, &c->scr_keys_out,
+                    &c->scr_vals_in, &c->scr_vals_out, &c->scr_seg, &c->scr_aos, &c->scr_event};
+  for (DevBuf *b : bufs)
+    if (b->p) cudaFree(b->p);
+  void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
+                  c->d_results, c->work.base, c->census.base, c->d_desc, c->d_counters};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto &ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int bgpu_set_cell_data(bgpu_ctx *c, const double *f, const double *op_a, const double *op_s) {
+  if (!c || !f || !op_a || !op_s) return fail(c, "bgpu_set_cell_data: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells;
+  CU(c, cudaMemcpyAsync(c->d_f, f, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_cell_stage, op_a, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_cell_stage + nc, op_s, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  k_expand_groups<<<grid_for(nc * c->mesh.G, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_cell_stage,
+                                                                        c->d_cell_stage + nc, c->d_opa, c->d_ops);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));  // the host arrays may be rewritten as soon as we return
+  c->have_cell_data = true;
+  return 0;
+}
+
+int bgpu_set_cell_groups(bgpu_ctx *c, const double *f, const double *abs_groups, const double *sct_groups) {
+  if (!c || !f || !abs_groups || !sct_groups) return fail(c, "bgpu_set_cell_groups: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells, G = c->mesh.G;
+  CU(c, cudaMemcpyAsync(c->d_f, f, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_opa, abs_groups, 8 * nc * G, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_ops, sct_groups, 8 * nc * G, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->have_cell_data = true;
+  return 0;
+}
+
+int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission, const double *E_source,
+                const double *E_census, double total_E, uint64_t *n_new_out, uint64_t *n_total_out) {
+  if (!c || !E_emission || !E_source) return fail(c, "bgpu_source: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint32_t nc = c->mesh.n_cells;
+  CU(c, cudaEventRecord(c->ev[0], c->stream));
+  double *dE = c->d_cell_stage;
+  CU(c, cudaMemcpyAsync(dE, E_emission, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(dE + nc, E_source, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  if (E_census) CU(c, cudaMemcpyAsync(dE + 2ull * nc, E_census, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  if (ensure(c, c->scr_counts, 4ull * 3 * nc)) return 1;
+  if (ensure(c, c->scr_offsets, 8ull * (3ull * nc + 2))) return 1;
+  uint32_t *cnt2 = (uint32_t *)c->scr_counts.p, *cnt1 = cnt2 + 2ull * nc;
+  uint64_t *off2 = (uint64_t *)c->scr_offsets.p, *off1 = off2 + 2ull * nc + 1;
+  k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 2, dE, dE + nc, c->n_user, total_E, cnt2);
+  if (device_scan(c, cnt2, 2ull * nc, off2)) return 1;
+  uint64_t n_new = 0, n_init = 0;
+  CU(c, cudaMemcpyAsync(&n_new, off2 + 2ull * nc, 8, cudaMemcpyDeviceToHost, c->stream));
+  if (E_census) {
+    k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 1, dE + 2ull * nc, nullptr, c->n_user, total_E, cnt1);
+    if (device_scan(c, cnt1, nc, off1)) return 1;
+    CU(c, cudaMemcpyAsync(&n_init, off1 + nc, 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  // cycle 1: the initial census replaces whatever census was there (census_photons = make_initial_census_photons)
+  const uint64_t n_cen = E_census ? n_init : c->n_census;
+  const uint64_t n_total = n_new + n_cen;
+  if (n_total >= (1ull << 32)) return fail(c, "bgpu_source: %llu photons exceed the reference's 2^32 limit", (unsigned long long)n_total);
+  if (ensure_work(c, n_total, 0)) return 1;
+  SourceParams S{};
+  S.ph = c->work;
+  S.mesh = c->mesh;
+  S.ctr_hi = c->ctr_hi;
+  S.dt = dt;
+  if (n_new) {
+    S.dst_offset = 0;
+    S.n = n_new;
+    S.offsets = off2;
+    S.n_entries = 2 * nc;
+    S.kinds = 2;
+    S.E0 = dE;
+    S.E1 = dE + nc;
+    // src/source.h:221-222
+    S.stream_base = 10000000000000ULL * (uint64_t)cycle + c->n_user * (uint64_t)c->rank;
+    k_source_sample<<<grid_for(n_new, 256), 256, 0, c->stream>>>(S);
+  }
+  if (E_census) {
+    if (n_init) {
+      S.dst_offset = n_new;
+      S.n = n_init;
+      S.offsets = off1;
+      S.n_entries = nc;
+      S.kinds = 1;
+      S.E0 = dE + 2ull * nc;
+      S.E1 = nullptr;
+      S.stream_base = c->n_user * (uint64_t)c->rank;  // src/source.h:144
+      k_source_sample<<<grid_for(n_init, 256), 256, 0, c->stream>>>(S);
+    }
+  } else if (n_cen) {
+    // join_photon_arrays: all = [new ..., census ...] (src/census_functions.h:21-29)
+    k_copy_soa<<<grid_for(n_cen, 256), 256, 0, c->stream>>>(c->census, 0, c->work, n_new, n_cen);
+  }
+  CU(c, cudaGetLastError());
+  c->n_new = n_new;
+  c->n_work = n_total;
+  // pre-transport census energy, get_photon_list_E (src/replicated_driver.h:61,71)
+  if (list_energy(c, c->work, n_new, n_cen, &c->pre_census_E)) return 1;
+  CU(c, cudaEventRecord(c->ev[1], c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->stats = bgpu_cycle_stats{};
+  c->stats.pre_census_E = c->pre_census_E;
+  c->stats.n_new = n_new;
+  c->stats.n_transported = n_total;
+  CU(c, cudaEventElapsedTime(&c->stats.ms_source, c->ev[0], c->ev[1]));
+  if (n_new_out) *n_new_out = n_new;
+  if (n_total_out) *n_total_out = n_total;
+  return 0;
+}
+
+int bgpu_transport(bgpu_ctx *c, double next_dt, int algorithm, int tally_mode) {
+  if (!c) return fail(c, "bgpu_transport: null ctx");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(c->ev[2], c->stream));
+  CU(c, cudaMemsetAsync(c->d_tally, 0, 16ull * c->mesh.n_cells, c->stream));
+  if (run_transport(c, algorithm, tally_mode, c->counters_on /* validation: full state of every photon */)) return 1;
+  CU(c, cudaEventRecord(c->ev[3], c->stream));
+  if (run_census(c, next_dt, tally_mode == BGPU_TALLY_DETERMINISTIC)) return 1;
+  CU(c, cudaEventRecord(c->ev[4], c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->stats.pre_census_E = c->pre_census_E;
+  c->stats.n_new = c->n_new;
+  c->stats.n_transported = c->n_work;
+  CU(c, cudaEventElapsedTime(&c->stats.ms_transport, c->ev[2], c->ev[3]));
+  CU(c, cudaEventElapsedTime(&c->stats.ms_census, c->ev[3], c->ev[4]));
+  c->stats.ms_total = c->stats.ms_source + c->stats.ms_transport + c->stats.ms_census;
+  c->stats_valid = true;
+  return 0;
+}
+
+int bgpu_get_tallies(bgpu_ctx *c, double *abs_E, double *track_E, bgpu_cycle_stats *stats) {
+  if (!c) return fail(c, "bgpu_get_tallies: null ctx");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells;
+  if (abs_E || track_E) {
+    if (ensure_pinned(c, 16 * nc)) return 1;
+    double *h = (double *)c->h_pinned;
+    CU(c, cudaMemcpyAsync(h, c->d_tally, 16 * nc, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (abs_E)
+      for (uint64_t i = 0; i < nc; ++i) abs_E[i] = h[2 * i];
+    if (track_E)
+      for (uint64_t i = 0; i < nc; ++i) track_E[i] = h[2 * i + 1];
+  }
+  if (stats) *stats = c->stats;
+  return 0;
+}
+
+int bgpu_tally_buffer(bgpu_ctx *c, uint64_t extra, void **device_ptr, uint64_t *n_doubles) {
+  if (!c || !device_ptr || !n_doubles) return fail(c, "bgpu_tally_buffer: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells;
+  if (extra > c->tally_extra) {
+    double *p = nullptr;
+    CU(c, cudaMalloc((void **)&p, 8 * (2 * nc + extra)));
+    CU(c, cudaMemcpyAsync(p, c->d_tally, 8 * (2 * nc + c->tally_extra), cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemsetAsync(p + 2 * nc + c->tally_extra, 0, 8 * (extra - c->tally_extra), c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaFree(c->d_tally));
+    c->d_tally = p;
+    c->tally_extra = extra;
+  }
+  *device_ptr = c->d_tally;
+  *n_doubles = 2 * nc + extra;
+  return 0;
+}
+
+int bgpu_sync(bgpu_ctx *c) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+void *bgpu_stream(bgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int bgpu_device(const bgpu_ctx *c) { return c ? c->device : -1; }
+
+int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cell_tallies, int algorithm,
+                               int tally_mode) {
+  if (!c || (!photons && n) || !cell_tallies) return fail(c, "bgpu_transport_photons_aos: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells;
+  if (n >= (1ull << 32)) return fail(c, "bgpu_transport_photons_aos: too many photons");
+  if (ensure_work(c, n, 0)) return 1;
+  if (ensure(c, c->scr_aos, 120 * n)) return 1;
+  CU(c, cudaMemcpyAsync(c->d_tally, cell_tallies, 16 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
+  c->n_work = n;
+  c->n_new = n;
+  if (n) {
+    CU(c, cudaMemcpyAsync(c->scr_aos.p, photons, 120 * n, cudaMemcpyHostToDevice, c->stream));
+    k_aos_to_soa<<<grid_for(n, 128), 128, 0, c->stream>>>((const uint64_t *)c->scr_aos.p, n, c->work, c->ctr_hi,
+                                                          c->d_stats);
+    unsigned long long bad = 0;
+    CU(c, cudaMemcpyAsync(&bad, c->d_stats + ST_BAD_RNG, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (bad)
+      return fail(c, "bgpu_transport_photons_aos: %llu photons carry an RNG seed/spawn word different from the ctx seed",
+                  bad);
+    if (run_transport(c, algorithm, tally_mode, true)) return 1;
+    k_soa_to_aos<<<grid_for(n, 128), 128, 0, c->stream>>>((uint64_t *)c->scr_aos.p, n, c->work, c->d_desc);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(photons, c->scr_aos.p, 120 * n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(c, cudaMemcpyAsync(cell_tallies, c->d_tally, 16 * nc, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+uint64_t bgpu_list_size(const bgpu_ctx *c, int which) {
+  if (!c) return 0;
+  return which == BGPU_LIST_CENSUS ? c->n_census : c->n_work;
+}
+
+int bgpu_enable_counters(bgpu_ctx *c, int on) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  c->counters_on = on != 0;
+  return ensure_work(c, c->work.cap, c->n_work);
+}
+
+int bgpu_set_launch(bgpu_ctx *c, int block_threads, int blocks_per_sm, int chunk) {
+  if (!c) return 1;
+  if (block_threads) {
+    if (block_threads != 128) return fail(c, "bgpu_set_launch: the transport kernel is built for 128-thread CTAs");
+    c->block_threads = block_threads;
+  }
+  c->blocks_per_sm = blocks_per_sm;
+  if (chunk > 0) c->chunk = (uint32_t)chunk;
+  return 0;
+}
+
+int bgpu_upload_photons(bgpu_ctx *c, int which, const bgpu_photon_soa *h) {
+  if (!c || !h) return fail(c, "bgpu_upload_photons: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t n = h->n;
+  if (n && (!h->cell || !h->group || !h->pos || !h->angle || !h->E || !h->E0 || !h->life_dx || !h->ctr || !h->stream))
+    return fail(c, "bgpu_upload_photons: every state field is required");
+  PhotonSoA *dst;
+  if (which == BGPU_LIST_CENSUS) {
+    if (ensure_soa(c, c->census, n, 0)) return 1;
+    dst = &c->census;
+    c->n_census = n;
+  } else {
+    if (ensure_work(c, n, 0)) return 1;
+    dst = &c->work;
+    c->n_work = n;
+    c->n_new = n;
+  }
+  if (!n) return 0;
+  std::vector<double2> a(n);
+  std::vector<ulonglong2> u(n);
+  auto put = [&](void *d, const void *s) { return cudaMemcpy(d, s, 16 * n, cudaMemcpyHostToDevice); };
+  for (uint64_t i = 0; i < n; ++i) a[i] = make_double2(h->pos[3 * i], h->pos[3 * i + 1]);
+  CU(c, put(dst->xy, a.data()));
+  for (uint64_t i = 0; i < n; ++i) a[i] = make_double2(h->pos[3 * i + 2], h->angle[3 * i]);
+  CU(c, put(dst->za, a.data()));
+  for (uint64_t i = 0; i < n; ++i) a[i] = make_double2(h->angle[3 * i + 1], h->angle[3 * i + 2]);
+  CU(c, put(dst->bc, a.data()));
+  for (uint64_t i = 0; i < n; ++i) a[i] = make_double2(h->E[i], h->E0[i]);
+  CU(c, put(dst->ee, a.data()));
+  for (uint64_t i = 0; i < n; ++i) {
+    unsigned long long bits;
+    memcpy(&bits, &h->life_dx[i], 8);
+    u[i] = make_ulonglong2(bits, h->ctr[i]);
+  }
+  CU(c, put(dst->lc, u.data()));
+  for (uint64_t i = 0; i < n; ++i)
+    u[i] = make_ulonglong2(h->stream[i], (unsigned long long)h->cell[i] | ((unsigned long long)h->group[i] << 32));
+  CU(c, put(dst->sg, u.data()));
+  return 0;
+}
+
+int bgpu_download_photons(bgpu_ctx *c, int which, bgpu_photon_soa *h) {
+  if (!c || !h) return fail(c, "bgpu_download_photons: null argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const PhotonSoA &src = (which == BGPU_LIST_CENSUS) ? c->census : c->work;
+  const uint64_t n = (which == BGPU_LIST_CENSUS) ? c->n_census : c->n_work;
+  if (h->n < n) return fail(c, "bgpu_download_photons: host arrays hold %llu photons, list has %llu",
+                            (unsigned long long)h->n, (unsigned long long)n);
+  h->n = n;
+  if (!n) return 0;
+  std::vector<double2> a(n);
+  std::vector<ulonglong2> u(n);
+  auto get = [&](void *d, const void *s) { return cudaMemcpy(d, s, 16 * n, cudaMemcpyDeviceToHost); };
+  if (h->pos) {
+    CU(c, get(a.data(), src.xy));
+    for (uint64_t i = 0; i < n; ++i) { h->pos[3 * i] = a[i].x; h->pos[3 * i + 1] = a[i].y; }
+  }
+  if (h->pos || h->angle) {
+    CU(c, get(a.data(), src.za));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h->pos) h->pos[3 * i + 2] = a[i].x;
+      if (h->angle) h->angle[3 * i] = a[i].y;
+    }
+  }
+  if (h->angle) {
+    CU(c, get(a.data(), src.bc));
+    for (uint64_t i = 0; i < n; ++i) { h->angle[3 * i + 1] = a[i].x; h->angle[3 * i + 2] = a[i].y; }
+  }
+  if (h->E || h->E0) {
+    CU(c, get(a.data(), src.ee));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h->E) h->E[i] = a[i].x;
+      if (h->E0) h->E0[i] = a[i].y;
+    }
+  }
+  if (h->life_dx || h->ctr) {
+    CU(c, get(u.data(), src.lc));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h->life_dx) memcpy(&h->life_dx[i], &u[i].x, 8);
+      if (h->ctr) h->ctr[i] = u[i].y;
+    }
+  }
+  if (h->stream || h->cell || h->group) {
+    CU(c, get(u.data(), src.sg));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h->stream) h->stream[i] = u[i].x;
+      if (h->cell) h->cell[i] = (uint32_t)u[i].y;
+      if (h->group) h->group[i] = (uint32_t)(u[i].y >> 32);
+    }
+  }
+  if (which == BGPU_LIST_WORK) {
+    if (h->descriptor) CU(c, cudaMemcpy(h->descriptor, c->d_desc, n, cudaMemcpyDeviceToHost));
+    if (h->counters) {
+      if (!c->counters_on || !c->d_counters) return fail(c, "bgpu_download_photons: counters were not enabled");
+      CU(c, cudaMemcpy(h->counters, c->d_counters, 16 * n, cudaMemcpyDeviceToHost));
+    }
+  }
+  return 0;
+}
+
+// known-answer hook for the RNG unit tests: out[i] = i-th draw of RNG(seed, stream) (src/RNG.h:318-330)
+__global__ void k_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *out) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint64_t ctr = 0;
+  for (uint32_t i = 0; i < n; ++i) out[i] = rng_next(ctr, ((uint64_t)seed) << 32, stream);
+}
+__global__ void k_threefry_kat(const uint64_t *in, uint64_t *out) {
+  if (threadIdx.x || blockIdx.x) return;
+  threefry2x64_20(in, in + 2, out);
+}
+int bgpu_test_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *out) {
+  double *d = nullptr;
+  if (cudaMalloc((void **)&d, 8ull * n) != cudaSuccess) return 1;
+  k_rng_draws<<<1, 32>>>(seed, stream, n, d);
+  const cudaError_t e = cudaMemcpy(out, d, 8ull * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e != cudaSuccess;
+}
+int bgpu_test_threefry(const uint64_t ctr_key[4], uint64_t out[2]) {
+  uint64_t *d = nullptr;
+  if (cudaMalloc((void **)&d, 48) != cudaSuccess) return 1;
+  cudaMemcpy(d, ctr_key, 32, cudaMemcpyHostToDevice);
+  k_threefry_kat<<<1, 32>>>(d, d + 4);
+  const cudaError_t e = cudaMemcpy(out, d + 4, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e != cudaSuccess;
+}
+
+}  // extern "C"

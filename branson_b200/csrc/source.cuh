@@ -1,0 +1,151 @@
+// source.cuh -- photon creation on the device.
+//
+// Replaces the serial host loops make_photons (reference src/source.h:212-366) and make_initial_census_photons
+// (:138-204).  The reference walks cells in mesh order and gives the k-th photon it creates the RNG stream
+// `cycle_offset + rank_offset + k` (:221-222,:267,:283; initial census: rank_offset + k, :144,:171).  Here:
+//   1. k_source_count   per cell: n = max(1, int(n_user * E_cell / total_E)) for E_cell > 0 (:230-233), the same
+//                       IEEE double expression, so counts are identical;
+//   2. exclusive scan   over the cell-major [emission, source] count pairs -> first photon index of every entry;
+//   3. k_source_sample  one thread per photon: binary search of its entry, then exactly the reference's draw order
+//                       get_emission_photon (:84-97) pos x,y,z -> angle (2) -> life_dx -> group = 7 draws,
+//                       get_boundary_source_photon (:100-114) face pos (2) -> cosine-law angle (2) -> life_dx -> group,
+//                       get_initial_census_photon (:117-131) pos (3) -> angle (2) -> group, life_dx = c*dt.
+#pragma once
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace bg {
+
+__device__ __forceinline__ uint32_t photons_for_cell(uint64_t n_user, double E, double total_E) {
+  // uint32_t t = int(n_user_photons * E / total_E); if (t == 0) t = 1;   (src/source.h:230-233)
+  uint32_t n = (uint32_t)(int)((double)n_user * E / total_E);
+  return n == 0 ? 1u : n;
+}
+
+// entries: [2*cell] = emission photons, [2*cell+1] = boundary-source photons (kinds == 2)
+//          [cell]   = initial census photons (kinds == 1)
+__global__ void k_source_count(uint32_t n_cells, int kinds, const double *__restrict__ E0,
+                               const double *__restrict__ E1, uint64_t n_user, double total_E,
+                               uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  const double e0 = E0[i];
+  const uint32_t c0 = (e0 > 0.0) ? photons_for_cell(n_user, e0, total_E) : 0u;
+  if (kinds == 1) {
+    counts[i] = c0;
+  } else {
+    const double e1 = E1[i];
+    const uint32_t c1 = (e1 > 0.0) ? photons_for_cell(n_user, e1, total_E) : 0u;
+    reinterpret_cast<uint2 *>(counts)[i] = make_uint2(c0, c1);
+  }
+}
+
+struct SourceParams {
+  PhotonSoA ph;
+  uint64_t dst_offset;   // first slot in ph to write
+  uint64_t n;            // photons to make
+  const uint64_t *offsets;  // exclusive scan of counts, n_entries + 1 values
+  uint32_t n_entries;
+  int kinds;             // 2: emission + boundary source, 1: initial census
+  const double *E0, *E1;
+  MeshDev mesh;
+  uint64_t ctr_hi;
+  uint64_t stream_base;  // cycle offset + rank offset
+  double dt;
+};
+
+__device__ __forceinline__ void uniform_angle(uint64_t &ctr, uint64_t ctr_hi, uint64_t stream, double &ax, double &ay,
+                                              double &az) {
+  // src/sampling_functions.h:57-70
+  const double mu = rng_next(ctr, ctr_hi, stream) * 2.0 - 1.0;
+  const double phi = rng_next(ctr, ctr_hi, stream) * 2.0 * K_PI;
+  const double sin_theta = sqrt(1.0 - mu * mu);
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  ax = sin_theta * cp;
+  ay = sin_theta * sp;
+  az = mu;
+}
+
+__global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n) return;
+  // entry e with offsets[e] <= k < offsets[e+1]
+  uint32_t lo = 0, hi = P.n_entries;  // invariant: offsets[lo] <= k < offsets[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(&P.offsets[mid]) <= k) lo = mid; else hi = mid;
+  }
+  const uint32_t entry = lo;
+  const uint32_t cell = (P.kinds == 2) ? (entry >> 1) : entry;
+  const bool boundary_source = (P.kinds == 2) && (entry & 1u);
+  const uint32_t n_in_entry = (uint32_t)(__ldg(&P.offsets[entry + 1]) - __ldg(&P.offsets[entry]));
+  const double E_cell = boundary_source ? P.E1[cell] : P.E0[cell];
+  const double E = E_cell / n_in_entry;
+
+  const uint32_t nx = P.mesh.nx, ny = P.mesh.ny;
+  const uint32_t sxy = nx * ny;
+  const uint32_t kk = cell / sxy, rem = cell - kk * sxy, jj = rem / nx, ii = rem - jj * nx;
+  const double *fx = P.mesh.faces, *fy = fx + (nx + 1), *fz = fy + (ny + 1);
+  const double x0 = __ldg(&fx[ii]), x1 = __ldg(&fx[ii + 1]);
+  const double y0 = __ldg(&fy[jj]), y1 = __ldg(&fy[jj + 1]);
+  const double z0 = __ldg(&fz[kk]), z1 = __ldg(&fz[kk + 1]);
+
+  const uint64_t ctr_hi = P.ctr_hi;
+  const uint64_t stream = P.stream_base + k;
+  uint64_t ctr = 0;
+  double x, y, z, ax, ay, az, life;
+  if (!boundary_source) {
+    // get_uniform_position_in_cell (src/sampling_functions.h:22-29)
+    x = x0 + rng_next(ctr, ctr_hi, stream) * (x1 - x0);
+    y = y0 + rng_next(ctr, ctr_hi, stream) * (y1 - y0);
+    z = z0 + rng_next(ctr, ctr_hi, stream) * (z1 - z0);
+    uniform_angle(ctr, ctr_hi, stream, ax, ay, az);
+  } else {
+    // Cell::get_source_face (src/cell.h:69-76): first face whose bc is SOURCE
+    int face = -1;
+    {
+      const bool on[6] = {ii == 0, ii == nx - 1, jj == 0, jj == ny - 1, kk == 0, kk == P.mesh.nz - 1};
+#pragma unroll
+      for (int s = 5; s >= 0; --s)
+        if (on[s] && P.mesh.bc[s] == BC_SOURCE) face = s;
+    }
+    // get_uniform_position_on_face (src/sampling_functions.h:32-52)
+    if (face == 0 || face == 1) {
+      x = (face == 0) ? x0 : x1;
+      y = y0 + rng_next(ctr, ctr_hi, stream) * (y1 - y0);
+      z = z0 + rng_next(ctr, ctr_hi, stream) * (z1 - z0);
+    } else if (face == 2 || face == 3) {
+      x = x0 + rng_next(ctr, ctr_hi, stream) * (x1 - x0);
+      y = (face == 2) ? y0 : y1;
+      z = z0 + rng_next(ctr, ctr_hi, stream) * (z1 - z0);
+    } else {
+      x = x0 + rng_next(ctr, ctr_hi, stream) * (x1 - x0);
+      y = y0 + rng_next(ctr, ctr_hi, stream) * (y1 - y0);
+      z = (face == 4) ? z0 : z1;
+    }
+    // get_source_angle_on_face (src/sampling_functions.h:94-121), signs exactly as the reference has them
+    const double theta = acos(sqrt(rng_next(ctr, ctr_hi, stream)));
+    const double phi = rng_next(ctr, ctr_hi, stream) * 2.0 * K_PI;
+    const double sign = (face % 2) ? -1.0 : 1.0;
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    if (face == 0 || face == 1) { ax = ct * sign; ay = st * sp; az = st * cp; }
+    else if (face == 2 || face == 3) { ax = st * sp; ay = ct; az = st * cp; }
+    else { ax = st * cp; ay = st * sp; az = ct; }
+  }
+  if (P.kinds == 2) life = rng_next(ctr, ctr_hi, stream) * K_C * P.dt;
+  else life = K_C * P.dt;
+  const uint32_t group = (uint32_t)floor(rng_next(ctr, ctr_hi, stream) * (double)P.mesh.G);
+
+  const uint64_t o = P.dst_offset + k;
+  P.ph.xy[o] = make_double2(x, y);
+  P.ph.za[o] = make_double2(z, ax);
+  P.ph.bc[o] = make_double2(ay, az);
+  P.ph.ee[o] = make_double2(E, E);
+  P.ph.lc[o] = make_ulonglong2((unsigned long long)__double_as_longlong(life), ctr);
+  P.ph.sg[o] = make_ulonglong2(stream, (unsigned long long)cell | ((unsigned long long)group << 32));
+}
+
+}  // namespace bg

@@ -1,0 +1,265 @@
+"""ctypes binding of libbranson_gpu.so -- the C ABI declared in include/branson_gpu.h.
+
+This is harness plumbing for tests / bench: the product is the CUDA library and the C++ host driver.  There is no
+fallback of any kind: if the shared library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbranson_gpu.so")
+
+ABI_VERSION = 1
+HISTORY, EVENT = 0, 1
+TALLY_ATOMIC, TALLY_DETERMINISTIC = 0, 1
+LIST_WORK, LIST_CENSUS = 0, 1
+BC = {"REFLECT": 0, "VACUUM": 1, "ELEMENT": 2, "SOURCE": 3, "PROCESSOR": 4}
+EXIT, PASS, CENSUS, SCATTER, KILLED, BOUND = range(6)
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("n_groups", C.c_uint32), ("nx", C.c_uint32), ("ny", C.c_uint32),
+                ("nz", C.c_uint32), ("x_faces", C.c_void_p), ("y_faces", C.c_void_p), ("z_faces", C.c_void_p),
+                ("bc", C.c_int32 * 6), ("seed", C.c_uint32), ("n_user_photons", C.c_uint64), ("rank", C.c_int32),
+                ("n_ranks", C.c_int32), ("device", C.c_int32), ("photon_capacity", C.c_uint64)]
+
+
+class CycleStats(C.Structure):
+    _fields_ = [("census_E", C.c_double), ("exit_E", C.c_double), ("pre_census_E", C.c_double),
+                ("n_new", C.c_uint64), ("n_transported", C.c_uint64), ("n_census", C.c_uint64),
+                ("n_killed", C.c_uint64), ("n_exit", C.c_uint64), ("n_events", C.c_uint64),
+                ("n_scatters", C.c_uint64), ("n_crossings", C.c_uint64), ("n_reflections", C.c_uint64),
+                ("n_deposits", C.c_uint64), ("n_group_lookups", C.c_uint64), ("ms_source", C.c_float),
+                ("ms_transport", C.c_float), ("ms_census", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class PhotonSoA(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("cell", C.c_void_p), ("group", C.c_void_p), ("pos", C.c_void_p),
+                ("angle", C.c_void_p), ("E", C.c_void_p), ("E0", C.c_void_p), ("life_dx", C.c_void_p),
+                ("ctr", C.c_void_p), ("stream", C.c_void_p), ("descriptor", C.c_void_p), ("counters", C.c_void_p)]
+
+
+_LIB = None
+
+EXPORTS = [
+    "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
+    "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
+    "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_test_rng_draws", "bgpu_test_threefry",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C branson_b200/csrc` "
+                               "(__graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
+        L.bgpu_device_count.restype = i32
+        L.bgpu_last_error.restype = C.c_char_p
+        L.bgpu_last_error.argtypes = [vp]
+        L.bgpu_create.argtypes = [C.POINTER(vp), C.POINTER(MeshDesc)]
+        L.bgpu_destroy.argtypes = [vp]
+        L.bgpu_destroy.restype = None
+        L.bgpu_set_cell_data.argtypes = [vp, vp, vp, vp]
+        L.bgpu_set_cell_groups.argtypes = [vp, vp, vp, vp]
+        L.bgpu_source.argtypes = [vp, u32, dbl, vp, vp, vp, dbl, C.POINTER(u64), C.POINTER(u64)]
+        L.bgpu_transport.argtypes = [vp, dbl, i32, i32]
+        L.bgpu_get_tallies.argtypes = [vp, vp, vp, C.POINTER(CycleStats)]
+        L.bgpu_tally_buffer.argtypes = [vp, u64, C.POINTER(vp), C.POINTER(u64)]
+        L.bgpu_sync.argtypes = [vp]
+        L.bgpu_stream.argtypes = [vp]
+        L.bgpu_stream.restype = vp
+        L.bgpu_device.argtypes = [vp]
+        L.bgpu_transport_photons_aos.argtypes = [vp, vp, u64, vp, i32, i32]
+        L.bgpu_upload_photons.argtypes = [vp, i32, C.POINTER(PhotonSoA)]
+        L.bgpu_download_photons.argtypes = [vp, i32, C.POINTER(PhotonSoA)]
+        L.bgpu_list_size.argtypes = [vp, i32]
+        L.bgpu_list_size.restype = u64
+        L.bgpu_enable_counters.argtypes = [vp, i32]
+        L.bgpu_set_launch.argtypes = [vp, i32, i32, i32]
+        L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
+        L.bgpu_test_threefry.argtypes = [vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class GpuError(RuntimeError):
+    pass
+
+
+def faces_from_nodes(nodes: np.ndarray, nx: int, ny: int, nz: int):
+    """Per-axis face arrays from the reference's per-cell node table [n_cells][6] (src/proto_mesh.h:106-218)."""
+    nodes = np.asarray(nodes, np.float64).reshape(-1, 6)
+    xf = np.concatenate([nodes[:nx, 0], nodes[nx - 1:nx, 1]])
+    yf = np.concatenate([nodes[0:nx * ny:nx, 2], nodes[nx * (ny - 1):nx * (ny - 1) + 1, 3]])
+    zf = np.concatenate([nodes[0::nx * ny, 4], nodes[nx * ny * (nz - 1):nx * ny * (nz - 1) + 1, 5]])
+    return xf.copy(), yf.copy(), zf.copy()
+
+
+class Context:
+    """One device context (bgpu_ctx)."""
+
+    def __init__(self, n_groups, nx, ny, nz, x_faces, y_faces, z_faces, bc, seed, n_user_photons, rank=0, n_ranks=1,
+                 device=-1, photon_capacity=0):
+        L = lib()
+        self._keep = [_f64(x_faces), _f64(y_faces), _f64(z_faces)]
+        assert len(self._keep[0]) == nx + 1 and len(self._keep[1]) == ny + 1 and len(self._keep[2]) == nz + 1
+        d = MeshDesc()
+        d.abi_version, d.n_groups, d.nx, d.ny, d.nz = ABI_VERSION, n_groups, nx, ny, nz
+        d.x_faces, d.y_faces, d.z_faces = (_ptr(a) for a in self._keep)
+        for i, b in enumerate(bc):
+            d.bc[i] = BC[b] if isinstance(b, str) else int(b)
+        d.seed, d.n_user_photons, d.rank, d.n_ranks, d.device = seed, n_user_photons, rank, n_ranks, device
+        d.photon_capacity = photon_capacity
+        h = C.c_void_p()
+        if L.bgpu_create(C.byref(h), C.byref(d)):
+            raise GpuError(L.bgpu_last_error(None).decode())
+        self._h = h
+        self.n_cells = nx * ny * nz
+        self.n_groups = n_groups
+
+    def _ck(self, rc):
+        if rc:
+            raise GpuError(lib().bgpu_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().bgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_cell_data(self, f, op_a, op_s):
+        f, a, s = _f64(f), _f64(op_a), _f64(op_s)
+        assert f.size == a.size == s.size == self.n_cells
+        self._ck(lib().bgpu_set_cell_data(self._h, _ptr(f), _ptr(a), _ptr(s)))
+
+    def set_cell_groups(self, f, abs_groups, sct_groups):
+        f, a, s = _f64(f), _f64(abs_groups), _f64(sct_groups)
+        assert f.size == self.n_cells and a.size == s.size == self.n_cells * self.n_groups
+        self._ck(lib().bgpu_set_cell_groups(self._h, _ptr(f), _ptr(a), _ptr(s)))
+
+    def source(self, cycle, dt, E_emission, E_source, E_census, total_E):
+        em, so = _f64(E_emission), _f64(E_source)
+        ce = _f64(E_census) if E_census is not None else None
+        n_new, n_tot = C.c_uint64(), C.c_uint64()
+        self._ck(lib().bgpu_source(self._h, cycle, dt, _ptr(em), _ptr(so), _ptr(ce), total_E, C.byref(n_new),
+                                   C.byref(n_tot)))
+        return n_new.value, n_tot.value
+
+    def transport(self, next_dt, algorithm=HISTORY, tally_mode=TALLY_ATOMIC):
+        self._ck(lib().bgpu_transport(self._h, next_dt, algorithm, tally_mode))
+
+    def tallies(self):
+        a, t = np.zeros(self.n_cells), np.zeros(self.n_cells)
+        st = CycleStats()
+        self._ck(lib().bgpu_get_tallies(self._h, _ptr(a), _ptr(t), C.byref(st)))
+        return a, t, st.as_dict()
+
+    def stats(self):
+        st = CycleStats()
+        self._ck(lib().bgpu_get_tallies(self._h, None, None, C.byref(st)))
+        return st.as_dict()
+
+    def tally_buffer(self, extra=0):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(lib().bgpu_tally_buffer(self._h, extra, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def sync(self):
+        self._ck(lib().bgpu_sync(self._h))
+
+    @property
+    def device(self):
+        return lib().bgpu_device(self._h)
+
+    def enable_counters(self, on=True):
+        self._ck(lib().bgpu_enable_counters(self._h, 1 if on else 0))
+
+    def set_launch(self, block_threads=0, blocks_per_sm=0, chunk=0):
+        self._ck(lib().bgpu_set_launch(self._h, block_threads, blocks_per_sm, chunk))
+
+    def list_size(self, which=LIST_WORK):
+        return lib().bgpu_list_size(self._h, which)
+
+    def upload(self, which, cell, group, pos, angle, E, E0, life_dx, ctr, stream):
+        n = len(cell)
+        arrs = dict(cell=np.ascontiguousarray(cell, np.uint32), group=np.ascontiguousarray(group, np.uint32),
+                    pos=_f64(pos).reshape(-1), angle=_f64(angle).reshape(-1), E=_f64(E), E0=_f64(E0),
+                    life_dx=_f64(life_dx), ctr=np.ascontiguousarray(ctr, np.uint64),
+                    stream=np.ascontiguousarray(stream, np.uint64))
+        s = PhotonSoA()
+        s.n = n
+        for k, v in arrs.items():
+            setattr(s, k, _ptr(v))
+        self._ck(lib().bgpu_upload_photons(self._h, which, C.byref(s)))
+
+    def download(self, which=LIST_WORK, counters=False):
+        n = self.list_size(which)
+        out = dict(cell=np.zeros(n, np.uint32), group=np.zeros(n, np.uint32), pos=np.zeros(3 * n), angle=np.zeros(3 * n),
+                   E=np.zeros(n), E0=np.zeros(n), life_dx=np.zeros(n), ctr=np.zeros(n, np.uint64),
+                   stream=np.zeros(n, np.uint64))
+        if which == LIST_WORK:
+            out["descriptor"] = np.zeros(n, np.uint8)
+            if counters:
+                out["counters"] = np.zeros(4 * n, np.uint32)
+        s = PhotonSoA()
+        s.n = n
+        for k, v in out.items():
+            setattr(s, k, _ptr(v))
+        self._ck(lib().bgpu_download_photons(self._h, which, C.byref(s)))
+        return out
+
+    def transport_photons_aos(self, photons: np.ndarray, cell_tallies: np.ndarray, algorithm=HISTORY,
+                              tally_mode=TALLY_ATOMIC):
+        """Drop-in for gpu_transport_photons: `photons` = uint8 array of 120-byte reference Photon records,
+        `cell_tallies` = float64 [n_cells][2]; both updated in place."""
+        assert photons.dtype == np.uint8 and photons.flags.c_contiguous and photons.size % 120 == 0
+        assert cell_tallies.dtype == np.float64 and cell_tallies.size == 2 * self.n_cells
+        self._ck(lib().bgpu_transport_photons_aos(self._h, _ptr(photons), photons.size // 120, _ptr(cell_tallies),
+                                                  algorithm, tally_mode))
+
+
+def context_for_deck(deck, nodes, seed=None, n_user_photons=None, rank=0, n_ranks=1, device=-1, **kw) -> Context:
+    nx, ny, nz = deck.n_cells_xyz
+    xf, yf, zf = faces_from_nodes(nodes, nx, ny, nz)
+    return Context(deck.n_groups, nx, ny, nz, xf, yf, zf, deck.bc, deck.seed if seed is None else seed,
+                   deck.photons if n_user_photons is None else n_user_photons, rank=rank, n_ranks=n_ranks,
+                   device=device, **kw)
+
+
+def rng_draws(seed, stream, n):
+    out = np.zeros(n)
+    if lib().bgpu_test_rng_draws(seed, stream, n, _ptr(out)):
+        raise GpuError("bgpu_test_rng_draws failed")
+    return out
+
+
+def threefry(ctr, key):
+    ck = np.array(list(ctr) + list(key), np.uint64)
+    out = np.zeros(2, np.uint64)
+    if lib().bgpu_test_threefry(_ptr(ck), _ptr(out)):
+        raise GpuError("bgpu_test_threefry failed")
+    return int(out[0]), int(out[1])

@@ -1,0 +1,167 @@
+/* branson_gpu.h -- C ABI of the B200 (sm_100a) IMC photon-transport hot path.
+ *
+ * This is the drop-in boundary for the part of lanl/branson that sits between
+ * `imc_replicated_driver` (reference src/replicated_driver.h:64-88) and the
+ * per-photon history loop (reference src/history_based_transport.h).  The
+ * reference has no FFI layer: its "operator API" for this path is the set of
+ * header calls
+ *
+ *   GPU_Setup(rank, n_ranks, use_gpu, cells)              src/gpu_setup.h:19-40
+ *   make_initial_census_photons<Census_T>(...)             src/source.h:138-204
+ *   make_photons<Census_T>(...)                            src/source.h:212-366
+ *   join_photon_arrays(all, census)                        src/census_functions.h:21-29
+ *   replicated_transport<Census_T>(...)                    src/replicated_transport.h:33-158
+ *     -> gpu_transport_photons(off, photons, cells, tallies) src/history_based_transport.h:348-413
+ *     -> post_process_photons(next_dt, ...)                src/post_process_functions.h:33-59
+ *   get_photon_list_E(census)                              src/census_functions.h:31-46
+ *
+ * Each entry point below names the reference call it replaces.  Only plain C
+ * types cross the boundary.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from bgpu_last_error() (the reference prints and MPI_Aborts,
+ *     src/config.h.in:86-91 -- the host driver does the same with our code);
+ *   - a bgpu_ctx owns all device memory of one device for the whole run; the
+ *     census stays resident in HBM between cycles;
+ *   - a ctx is not thread safe; one ctx per device, one host thread per ctx;
+ *   - there is NO CPU fallback: without a CUDA device bgpu_create fails.
+ */
+#ifndef BRANSON_GPU_H
+#define BRANSON_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGPU_ABI_VERSION 1
+
+/* Constants::bc_type, reference src/constants.h:28 */
+enum { BGPU_REFLECT = 0, BGPU_VACUUM = 1, BGPU_ELEMENT = 2, BGPU_SOURCE = 3, BGPU_PROCESSOR = 4 };
+/* Constants::event_type, reference src/constants.h:27 */
+enum { BGPU_EXIT = 0, BGPU_PASS = 1, BGPU_CENSUS = 2, BGPU_SCATTER = 3, BGPU_KILLED = 4, BGPU_BOUND = 5 };
+/* Constants::transport algorithm, reference src/constants.h (HISTORY / EVENT) */
+enum { BGPU_HISTORY = 0, BGPU_EVENT = 1 };
+/* tally reduction mode */
+enum {
+  BGPU_TALLY_ATOMIC = 0,       /* FP64 atomics (production) */
+  BGPU_TALLY_DETERMINISTIC = 1 /* deposit log -> stable sort by cell -> in-order sum == the reference's serial
+                                  photon-order summation (history_cpu_transport_photons with one thread) */
+};
+
+typedef struct bgpu_ctx bgpu_ctx;
+
+/* Replaces the per-cycle GPU_Setup cell upload (src/gpu_setup.h:23-40).  The reference mesh is a tensor-product
+ * grid (src/proto_mesh.h:106-218): cell = i + nx*(j + ny*k), cell bounds are the per-axis face arrays below,
+ * neighbours are +-1 / +-nx / +-nx*ny and only domain faces carry a non-ELEMENT boundary condition. */
+typedef struct {
+  uint32_t abi_version;  /* = BGPU_ABI_VERSION */
+  uint32_t n_groups;     /* BRANSON_N_GROUPS */
+  uint32_t nx, ny, nz;
+  const double *x_faces; /* [nx+1] */
+  const double *y_faces; /* [ny+1] */
+  const double *z_faces; /* [nz+1] */
+  int32_t bc[6];         /* X_NEG X_POS Y_NEG Y_POS Z_NEG Z_POS */
+  uint32_t seed;         /* IMC_Parameters::get_rng_seed */
+  uint64_t n_user_photons;
+  int32_t rank, n_ranks; /* replicated-mode rank of this device (stream offsets, src/source.h:144,221-222) */
+  int32_t device;        /* CUDA device ordinal; <0: rank % n_devices (src/gpu_setup.h:68-78) */
+  uint64_t photon_capacity; /* initial capacity hint (0 = 1.25 * n_user_photons / n_ranks); grows on demand */
+} bgpu_mesh_desc;
+
+/* per-cycle results: feeds IMC_State::set_* (src/replicated_transport.h:151-155, src/replicated_driver.h:61,71,80) */
+typedef struct {
+  double census_E;      /* post-transport census energy */
+  double exit_E;
+  double pre_census_E;  /* get_photon_list_E of the census entering this cycle */
+  uint64_t n_new;       /* photons created by make_photons this cycle */
+  uint64_t n_transported; /* all_photons.size() */
+  uint64_t n_census;    /* census_list.size() after transport */
+  uint64_t n_killed, n_exit;
+  /* exact event counts of the cycle (for the algorithmic-bytes roofline) */
+  uint64_t n_events, n_scatters, n_crossings, n_reflections, n_deposits, n_group_lookups;
+  /* device times (CUDA events on the ctx stream), milliseconds */
+  float ms_source, ms_transport, ms_census, ms_total;
+} bgpu_cycle_stats;
+
+/* host-side SoA view used by bgpu_upload_photons / bgpu_download_photons (validation and tests).  Any pointer may be
+ * NULL on download to skip that field.  pos/angle are [n][3]. */
+typedef struct {
+  uint64_t n;
+  uint32_t *cell, *group;
+  double *pos, *angle, *E, *E0, *life_dx;
+  uint64_t *ctr;    /* RNG counter low word == number of draws consumed (src/RNG.h:262-285) */
+  uint64_t *stream; /* RNG key low word (src/RNG.h:318-330) */
+  uint8_t *descriptor;
+  uint32_t *counters; /* [n][4] events, scatters, cell crossings, reflections (only if counters were enabled) */
+} bgpu_photon_soa;
+
+int bgpu_device_count(void);
+const char *bgpu_last_error(const bgpu_ctx *ctx); /* ctx may be NULL: error of the last failed bgpu_create */
+
+/* GPU_Setup ctor (src/gpu_setup.h:19-40): picks the device, uploads the (static) geometry once. */
+int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *desc);
+void bgpu_destroy(bgpu_ctx *ctx);
+
+/* The per-cycle part of GPU_Setup: Mesh::calculate_photon_energy rewrites op_a/op_s/f every cycle
+ * (src/mesh.h:253-270).  f, op_a, op_s are per-cell gray values [n_cells]; like Cell::set_op_a/set_op_s
+ * (src/cell.h:260-275) every group of a cell receives the same value. */
+int bgpu_set_cell_data(bgpu_ctx *ctx, const double *f, const double *op_a, const double *op_s);
+/* General multigroup form: abs_groups / sct_groups [n_cells][n_groups] (src/cell.h:318-337). */
+int bgpu_set_cell_groups(bgpu_ctx *ctx, const double *f, const double *abs_groups, const double *sct_groups);
+
+/* make_initial_census_photons (cycle 1 only, pass E_census != NULL; src/source.h:138-204) + make_photons
+ * (src/source.h:212-366) + join_photon_arrays (src/census_functions.h:21-29): after the call the device work list
+ * is [new photons ..., census ...].  E_* are this rank's per-cell source energies [n_cells] from
+ * Mesh::get_emission_E / get_source_E / get_census_E, total_E is the global source energy
+ * (src/replicated_driver.h:56-59), cycle is IMC_State::get_step(). */
+int bgpu_source(bgpu_ctx *ctx, uint32_t cycle, double dt, const double *E_emission, const double *E_source,
+                const double *E_census_or_null, double total_E, uint64_t *n_new, uint64_t *n_total);
+
+/* replicated_transport (src/replicated_transport.h:33-158) on the device work list: history loop, then
+ * post_process_photons (census compaction with life_dx = c*next_dt, exit/census energy sums).  Tallies are zeroed at
+ * entry (a fresh vector<Cell_Tally>, src/replicated_transport.h:71).
+ * algorithm: BGPU_HISTORY | BGPU_EVENT; tally_mode: BGPU_TALLY_ATOMIC | BGPU_TALLY_DETERMINISTIC. */
+int bgpu_transport(bgpu_ctx *ctx, double next_dt, int algorithm, int tally_mode);
+
+/* rank_abs_E / rank_track_E hand-off (src/replicated_transport.h:135-140); either pointer may be NULL. */
+int bgpu_get_tallies(bgpu_ctx *ctx, double *abs_E, double *track_E, bgpu_cycle_stats *stats);
+
+/* Packed device buffer for the end-of-cycle all-reduce (replaces the MPI_Allreduce calls of
+ * src/replicated_driver.h:91-94): n_doubles doubles = interleaved Cell_Tally {abs_E, track_E}[n_cells] followed by
+ * `extra` caller-owned doubles.  The caller all-reduces it in place (NCCL) and then calls bgpu_get_tallies. */
+int bgpu_tally_buffer(bgpu_ctx *ctx, uint64_t extra, void **device_ptr, uint64_t *n_doubles);
+/* cudaStreamSynchronize of the ctx stream / raw stream handle for collective plumbing */
+int bgpu_sync(bgpu_ctx *ctx);
+void *bgpu_stream(bgpu_ctx *ctx);
+int bgpu_device(const bgpu_ctx *ctx);
+
+/* Drop-in for gpu_transport_photons (src/history_based_transport.h:348-413): `photons` is the reference's host
+ * std::vector<Photon>::data() (120-byte records, src/photon.h:171-182), `cell_tallies` its vector<Cell_Tally>::data()
+ * (16-byte records, src/cell_tally.h:53-54).  Photons are updated in place exactly as transport_photon does and the
+ * tallies are ACCUMULATED into cell_tallies.  Cell data must have been set with bgpu_set_cell_data. */
+int bgpu_transport_photons_aos(bgpu_ctx *ctx, void *photons, uint64_t n_photons, void *cell_tallies,
+                               int algorithm, int tally_mode);
+
+/* validation / tests: replace or read the device work list (pre- or post-transport) and the census */
+enum { BGPU_LIST_WORK = 0, BGPU_LIST_CENSUS = 1 };
+int bgpu_upload_photons(bgpu_ctx *ctx, int which, const bgpu_photon_soa *host);
+int bgpu_download_photons(bgpu_ctx *ctx, int which, bgpu_photon_soa *host);
+uint64_t bgpu_list_size(const bgpu_ctx *ctx, int which);
+/* Validation mode: per-photon event counters (bit-exact observable) are recorded and EVERY photon's final state is
+ * written back (production writes the full state of CENSUS photons only, plus E and the descriptor of the rest). */
+int bgpu_enable_counters(bgpu_ctx *ctx, int on);
+
+/* tuning knobs (defaults chosen for B200: 148 SMs) */
+int bgpu_set_launch(bgpu_ctx *ctx, int block_threads, int blocks_per_sm, int chunk_photons);
+
+/* known-answer hooks for the RNG unit tests (RNG(seed, stream) draws, src/RNG.h:262-285,318-330; raw Threefry2x64-20
+ * of {ctr0, ctr1, key0, key1}, src/random123/threefry.h:196-282) */
+int bgpu_test_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *out);
+int bgpu_test_threefry(const uint64_t ctr_key[4], uint64_t out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRANSON_GPU_H */
