@@ -1,0 +1,171 @@
+// replicated_driver.h -- the replicated-mode cycle loop with the reference's driver shape (src/replicated_driver.h:33-122)
+// and its transport seam (src/replicated_transport.h:33-158), calling the device through the C ABI only.
+//
+// Per cycle, in the reference's order:
+//   mesh.calculate_photon_energy            (:53)   host, O(n_cells)
+//   all-reduce global source energy         (:56-59)
+//   GPU_Setup per-cycle part                (:64)   bgpu_set_cell_data: f, op_a, op_s -- 3 doubles per cell
+//   make_initial_census_photons / make_photons / join_photon_arrays (:68-75)   bgpu_source, on the device
+//   replicated_transport                    (:87-88) bgpu_transport: history loop + census compaction, on the device
+//   all-reduce abs_E / track_E              (:91-94) ONE in-place NCCL all-reduce of the packed device tally buffer
+//   mesh.update_temperature                 (:96)   host
+//   rank != 0 zeroes its material sums, print_conservation, next_time_step (:100-120)
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <iostream>
+#include <vector>
+
+#include "comm.h"
+#include "gpu_setup.h"
+#include "imc_parameters.h"
+#include "imc_state.h"
+#include "mesh.h"
+
+namespace branson {
+
+struct Cycle_Report {
+  uint32_t step;
+  double dt, time, next_dt, global_source_energy;
+  bgpu_cycle_stats gpu;  // this rank's device statistics
+  // wall-clock seconds of the host-visible phases of this cycle
+  double t_calc_energy, t_cell_upload, t_source, t_transport, t_allreduce, t_tally_download, t_update_T, t_cycle;
+};
+
+struct Driver_Options {
+  int tally_mode = BGPU_TALLY_ATOMIC;
+  bool print = true;
+};
+
+inline double wall_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// replicated_transport (src/replicated_transport.h:33-158): runs the device transport + post-processing, fills the
+// rank tallies and the IMC_State diagnostics.  The census stays on the device (the reference returns it by value).
+inline void replicated_transport(const Mesh &mesh, const GPU_Setup &gpu_setup, IMC_State &imc_state,
+                                 std::vector<double> &rank_abs_E, std::vector<double> &rank_track_E, const Comm &comm,
+                                 const int transport_algorithm, const int tally_mode, Cycle_Report &rep) {
+  const double next_dt = imc_state.get_next_dt();  // set for census photons (:52)
+  bgpu_ctx *ctx = gpu_setup.get_ctx();
+  const double t0 = wall_now();
+  gpu_setup.check(bgpu_transport(ctx, next_dt, transport_algorithm == Constants::EVENT ? BGPU_EVENT : BGPU_HISTORY,
+                                 tally_mode),
+                  "bgpu_transport");
+  const double t1 = wall_now();
+  rep.t_transport = t1 - t0;
+  // abs_E / track_E: summed over ranks on the device (NVLink), then handed to the host once
+  if (!comm.single()) {
+    if (comm.has_device_allreduce()) {
+      void *dptr = nullptr;
+      uint64_t n = 0;
+      gpu_setup.check(bgpu_tally_buffer(ctx, 0, &dptr, &n), "bgpu_tally_buffer");
+      comm.sum_device(dptr, n, bgpu_stream(ctx));
+    }
+  }
+  const double t2 = wall_now();
+  rep.t_allreduce = t2 - t1;
+  gpu_setup.check(bgpu_get_tallies(ctx, rank_abs_E.data(), rank_track_E.data(), &rep.gpu), "bgpu_get_tallies");
+  if (!comm.single() && !comm.has_device_allreduce()) {
+    // host fallback for the collective only (gloo in the CPU-side tests): same sums, host buffers
+    comm.sum(rank_abs_E.data(), rank_abs_E.size());
+    comm.sum(rank_track_E.data(), rank_track_E.size());
+  }
+  rep.t_tally_download = wall_now() - t2;
+  (void)mesh;
+  imc_state.set_exit_E(rep.gpu.exit_E);
+  imc_state.set_post_census_E(rep.gpu.census_E);
+  imc_state.set_census_size(rep.gpu.n_census);
+  imc_state.set_rank_transport_runtime(rep.t_transport);
+}
+
+class Replicated_Driver {
+public:
+  Replicated_Driver(Mesh &mesh_, IMC_State &imc_state_, const IMC_Parameters &imc_p_, const Comm &comm_,
+                    GPU_Setup &gpu_setup_, const Driver_Options &opt_)
+      : mesh(mesh_), imc_state(imc_state_), imc_p(imc_p_), comm(comm_), gpu_setup(gpu_setup_), opt(opt_),
+        abs_E(mesh_.get_n_global_cells(), 0.0), track_E(mesh_.get_n_global_cells(), 0.0) {}
+
+  bool finished() const { return imc_state.finished(); }
+
+  // one trip of the reference's while loop (src/replicated_driver.h:47-121)
+  Cycle_Report cycle() {
+    Cycle_Report rep{};
+    const int rank = comm.get_rank();
+    const double t_begin = wall_now();
+    rep.step = imc_state.get_step();
+    rep.dt = imc_state.get_dt();
+    rep.time = imc_state.get_time();
+    rep.next_dt = imc_state.get_next_dt();
+    if (rank == 0 && opt.print) imc_state.print_timestep_header();
+
+    mesh.calculate_photon_energy(imc_state, (uint32_t)imc_p.get_n_user_photons());
+    double global_source_energy = mesh.get_total_photon_E();
+    comm.sum(&global_source_energy, 1);
+    rep.global_source_energy = global_source_energy;
+    const double t1 = wall_now();
+    rep.t_calc_energy = t1 - t_begin;
+
+    bgpu_ctx *ctx = gpu_setup.get_ctx();
+    gpu_setup.check(bgpu_set_cell_data(ctx, mesh.get_f().data(), mesh.get_op_a().data(), mesh.get_op_s().data()),
+                    "bgpu_set_cell_data");
+    const double t2 = wall_now();
+    rep.t_cell_upload = t2 - t1;
+
+    uint64_t n_new = 0, n_total = 0;
+    gpu_setup.check(bgpu_source(ctx, imc_state.get_step(), imc_state.get_dt(), mesh.get_emission_E().data(),
+                                mesh.get_source_E().data(),
+                                imc_state.get_step() == 1 ? mesh.get_census_E().data() : nullptr,
+                                global_source_energy, &n_new, &n_total),
+                    "bgpu_source");
+    bgpu_cycle_stats st{};
+    gpu_setup.check(bgpu_get_tallies(ctx, nullptr, nullptr, &st), "bgpu_get_tallies");
+    imc_state.set_pre_census_E(st.pre_census_E);
+    const double t3 = wall_now();
+    rep.t_source = t3 - t2;
+    if (rank == 0 && opt.print) std::cout << "source time: " << rep.t_source << std::endl;
+    imc_state.set_transported_particles(n_total);
+
+    comm.barrier();
+    replicated_transport(mesh, gpu_setup, imc_state, abs_E, track_E, comm, (int)imc_p.get_transport_algorithm(),
+                         opt.tally_mode, rep);
+
+    const double t4 = wall_now();
+    last_abs_E = abs_E;
+    last_track_E = track_E;
+    mesh.update_temperature(abs_E, track_E, imc_state);
+    rep.t_update_T = wall_now() - t4;
+
+    comm.barrier();
+    if (rank) {  // for replicated, just let root do conservation (:100-104)
+      imc_state.set_absorbed_E(0.0);
+      imc_state.set_pre_mat_E(0.0);
+      imc_state.set_post_mat_E(0.0);
+    }
+    imc_state.print_conservation(comm, opt.print);
+    imc_state.next_time_step();
+    rep.t_cycle = wall_now() - t_begin;
+    return rep;
+  }
+
+  const std::vector<double> &get_last_abs_E() const { return last_abs_E; }
+  const std::vector<double> &get_last_track_E() const { return last_track_E; }
+
+private:
+  Mesh &mesh;
+  IMC_State &imc_state;
+  const IMC_Parameters &imc_p;
+  const Comm &comm;
+  GPU_Setup &gpu_setup;
+  Driver_Options opt;
+  std::vector<double> abs_E, track_E, last_abs_E, last_track_E;
+};
+
+// the reference's entry point: run all cycles (src/replicated_driver.h:33-122)
+inline void imc_replicated_driver(Mesh &mesh, IMC_State &imc_state, const IMC_Parameters &imc_parameters,
+                                  const Comm &comm, GPU_Setup &gpu_setup, const Driver_Options &opt = Driver_Options()) {
+  Replicated_Driver drv(mesh, imc_state, imc_parameters, comm, gpu_setup, opt);
+  while (!drv.finished()) drv.cycle();
+}
+
+}  // namespace branson

@@ -1,0 +1,248 @@
+"""ctypes binding of libbranson_host.so (include/branson_host.h): the C++ host layer -- Input, IMC_Parameters,
+IMC_State, Mesh and the replicated cycle driver -- stepped one cycle at a time.
+
+Harness plumbing only.  Multi-GPU: one process per GPU (torchrun); `TorchComm` hands torch.distributed collectives to
+the C++ driver, the tally all-reduce runs in place on the device buffer over NCCL / NVLink.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import gpu
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbranson_host.so")
+
+EXPORTS = ["bhost_create", "bhost_destroy", "bhost_last_error", "bhost_finished", "bhost_calculate_photon_energy",
+           "bhost_cycle", "bhost_next_time_step", "bhost_get_array", "bhost_get_param", "bhost_gpu_ctx", "bhost_total_transport_time"]
+
+_F_SUM = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_uint64)
+_F_SUMDEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+_F_SUMU = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64)
+_F_BAR = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class CommStruct(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("allreduce_sum_f64", _F_SUM), ("allreduce_sum_f64_device", _F_SUMDEV),
+                ("allreduce_sum_u64", _F_SUMU), ("allreduce_max_f64", _F_SUM), ("allreduce_min_f64", _F_SUM),
+                ("barrier", _F_BAR)]
+
+
+class Options(C.Structure):
+    _fields_ = [("n_groups", C.c_uint32), ("device", C.c_int32), ("tally_mode", C.c_int32), ("algorithm", C.c_int32),
+                ("print", C.c_int32), ("validate", C.c_int32), ("no_gpu", C.c_int32),
+                ("photons_override", C.c_uint64), ("t_stop_override", C.c_double), ("force_replicated", C.c_int32)]
+
+
+class CycleReport(C.Structure):
+    _fields_ = [("step", C.c_uint32), ("dt", C.c_double), ("time", C.c_double), ("next_dt", C.c_double),
+                ("global_source_energy", C.c_double), ("gpu", gpu.CycleStats),
+                ("t_calc_energy", C.c_double), ("t_cell_upload", C.c_double), ("t_source", C.c_double),
+                ("t_transport", C.c_double), ("t_allreduce", C.c_double), ("t_tally_download", C.c_double),
+                ("t_update_T", C.c_double), ("t_cycle", C.c_double),
+                ("absorbed_E", C.c_double), ("emission_E", C.c_double), ("source_E", C.c_double),
+                ("pre_census_E", C.c_double), ("post_census_E", C.c_double), ("pre_mat_E", C.c_double),
+                ("post_mat_E", C.c_double), ("exit_E", C.c_double), ("rad_conservation", C.c_double),
+                ("mat_conservation", C.c_double), ("trans_particles", C.c_uint64), ("census_size", C.c_uint64)]
+
+    def as_dict(self):
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = v.as_dict() if isinstance(v, gpu.CycleStats) else v
+        return d
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C branson_b200/csrc`")
+        gpu.lib()  # libbranson_gpu.so first (rpath $ORIGIN also finds it)
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.bhost_create.restype = vp
+        L.bhost_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(CommStruct), C.c_char_p,
+                                   C.c_size_t]
+        L.bhost_destroy.argtypes = [vp]
+        L.bhost_destroy.restype = None
+        L.bhost_last_error.argtypes = [vp]
+        L.bhost_last_error.restype = C.c_char_p
+        L.bhost_finished.argtypes = [vp]
+        L.bhost_calculate_photon_energy.argtypes = [vp, C.POINTER(C.c_double)]
+        L.bhost_cycle.argtypes = [vp, C.POINTER(CycleReport)]
+        L.bhost_next_time_step.argtypes = [vp]
+        L.bhost_get_array.argtypes = [vp, C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_uint64)]
+        L.bhost_get_param.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
+        L.bhost_gpu_ctx.argtypes = [vp]
+        L.bhost_gpu_ctx.restype = vp
+        L.bhost_total_transport_time.argtypes = [vp]
+        L.bhost_total_transport_time.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+class HostError(RuntimeError):
+    pass
+
+
+class TorchComm:
+    """torch.distributed collectives for the C++ driver (csrc/host/comm.h).  Host scalars travel through a small
+    tensor on `device` (cuda:N with NCCL, cpu with gloo); the tally buffer is all-reduced in place on the GPU."""
+
+    def __init__(self, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device_allreduce_bytes = 0
+        self._cbs = [_F_SUM(self._sum), _F_SUMDEV(self._sum_dev), _F_SUMU(self._sum_u64), _F_SUM(self._max),
+                     _F_SUM(self._min), _F_BAR(self._barrier)]
+        null_dev = C.cast(None, _F_SUMDEV)
+        self.struct = CommStruct(None, self._cbs[0], self._cbs[1] if self.device.type == "cuda" else null_dev,
+                                 self._cbs[2], self._cbs[3], self._cbs[4], self._cbs[5])
+
+    def _host_reduce(self, buf, n, dtype, np_dtype, op):
+        try:
+            a = np.ctypeslib.as_array(buf, shape=(n,))
+            t = self.torch.from_numpy(a.astype(np_dtype, copy=True)).to(self.device)
+            self.dist.all_reduce(t, op=op)
+            a[:] = t.cpu().numpy().astype(a.dtype)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print(f"TorchComm: {e}", flush=True)
+            return 1
+
+    def _sum(self, _u, buf, n):
+        return self._host_reduce(buf, n, None, np.float64, self.dist.ReduceOp.SUM)
+
+    def _max(self, _u, buf, n):
+        return self._host_reduce(buf, n, None, np.float64, self.dist.ReduceOp.MAX)
+
+    def _min(self, _u, buf, n):
+        return self._host_reduce(buf, n, None, np.float64, self.dist.ReduceOp.MIN)
+
+    def _sum_u64(self, _u, buf, n):
+        # counts stay far below 2^63: carried as int64
+        return self._host_reduce(buf, n, None, np.int64, self.dist.ReduceOp.SUM)
+
+    def _sum_dev(self, _u, dptr, n, _stream):
+        try:
+            t = device_tensor_f64(self.torch, dptr, n, self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            self.torch.cuda.synchronize(self.device)
+            self.device_allreduce_bytes += 8 * n
+            return 0
+        except Exception as e:  # pragma: no cover
+            print(f"TorchComm device all-reduce: {e}", flush=True)
+            return 1
+
+    def _barrier(self, _u):
+        try:
+            if self.device.type == "cuda":
+                self.dist.barrier(device_ids=[self.device.index])
+            else:
+                self.dist.barrier()
+            return 0
+        except Exception as e:  # pragma: no cover
+            print(f"TorchComm barrier: {e}", flush=True)
+            return 1
+
+
+def device_tensor_f64(torch, dptr: int, n: int, device):
+    """A torch float64 view of `n` doubles of device memory owned by the bgpu ctx (no copy)."""
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(dptr), False), "version": 3,
+                                    "strides": None}
+
+    return torch.as_tensor(_Arr(), device=device)
+
+
+class Driver:
+    """Replicated cycle driver for one rank / one GPU."""
+
+    def __init__(self, xml_path, n_groups=1, rank=0, n_ranks=1, device=-1, tally_mode=gpu.TALLY_ATOMIC, algorithm=-1,
+                 print_report=False, validate=False, no_gpu=False, photons=0, t_stop=0.0, force_replicated=False,
+                 comm: TorchComm | None = None):
+        L = lib()
+        o = Options(n_groups, device, tally_mode, algorithm, 1 if print_report else 0, 1 if validate else 0,
+                    1 if no_gpu else 0, photons, t_stop, 1 if force_replicated else 0)
+        err = C.create_string_buffer(1024)
+        self._comm = comm
+        self._h = L.bhost_create(str(xml_path).encode(), rank, n_ranks, C.byref(o),
+                                 C.byref(comm.struct) if comm is not None else None, err, 1024)
+        if not self._h:
+            raise HostError(err.value.decode())
+        self.n_groups = n_groups
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().bhost_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def finished(self) -> bool:
+        return bool(lib().bhost_finished(self._h))
+
+    def calculate_photon_energy(self) -> float:
+        g = C.c_double()
+        if lib().bhost_calculate_photon_energy(self._h, C.byref(g)):
+            raise HostError(lib().bhost_last_error(self._h).decode())
+        return g.value
+
+    def cycle(self) -> dict:
+        r = CycleReport()
+        if lib().bhost_cycle(self._h, C.byref(r)):
+            raise HostError(lib().bhost_last_error(self._h).decode())
+        return r.as_dict()
+
+    def next_time_step(self):
+        lib().bhost_next_time_step(self._h)
+
+    def array(self, name: str) -> np.ndarray:
+        p, n = C.POINTER(C.c_double)(), C.c_uint64()
+        if lib().bhost_get_array(self._h, name.encode(), C.byref(p), C.byref(n)):
+            raise KeyError(name)
+        if n.value == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def param(self, name: str) -> float:
+        v = C.c_double()
+        if lib().bhost_get_param(self._h, name.encode(), C.byref(v)):
+            raise KeyError(name)
+        return v.value
+
+    def gpu_context(self) -> "GpuView":
+        h = lib().bhost_gpu_ctx(self._h)
+        if not h:
+            raise HostError("driver was created without a GPU context")
+        return GpuView(h, int(self.param("n_cells")), self.n_groups)
+
+    def total_transport_time(self) -> float:
+        return lib().bhost_total_transport_time(self._h)
+
+
+class GpuView(gpu.Context):
+    """A non-owning gpu.Context over the driver's bgpu_ctx (photon dumps in validation runs)."""
+
+    def __init__(self, handle, n_cells, n_groups):  # noqa: super().__init__ intentionally not called
+        self._h = C.c_void_p(handle)
+        self.n_cells = n_cells
+        self.n_groups = n_groups
+
+    def close(self):
+        self._h = None

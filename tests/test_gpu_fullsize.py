@@ -1,0 +1,65 @@
+"""BASELINE-size runs on the GPU, checked through size-independent properties (the oracle would need minutes to
+hours here): exact photon bookkeeping, energy balance to 1e-12, deterministic-mode reproducibility against the atomic
+mode, and agreement of integer outcomes between work distributions."""
+import numpy as np
+import pytest
+
+from branson_b200 import decks, driver, gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(deck, tmp_path, cycles, **kw):
+    d = driver.Driver(deck.write(str(tmp_path / f"{deck.name}.xml")), n_groups=deck.n_groups, device=0, **kw)
+    reps, arrays = [], []
+    for _ in range(cycles):
+        reps.append(d.cycle())
+        arrays.append((d.array("abs_E"), d.array("track_E"), d.array("T_e")))
+    d.close()
+    return reps, arrays
+
+
+def _check_balance(reps):
+    for r in reps:
+        g = r["gpu"]
+        assert g["n_transported"] == g["n_killed"] + g["n_exit"] + g["n_census"]
+        assert g["n_deposits"] == g["n_crossings"] + g["n_transported"]
+        assert g["n_events"] >= g["n_scatters"] + g["n_crossings"] + g["n_reflections"]
+        total = r["pre_census_E"] + r["emission_E"] + r["source_E"]
+        assert abs(r["rad_conservation"]) <= 1e-12 * total, (r["step"], r["rad_conservation"], total)
+        assert abs(r["mat_conservation"]) <= 1e-12 * abs(r["post_mat_E"])
+
+
+def test_hohlraum_single_node_full_size(tmp_path):
+    # configs[2]: 65 x 65 x 140 cells, 30 groups, 1e7 photons (reference inputs/3D_hohlraum_single_node.xml)
+    deck = decks.hohlraum_single(t_stop=0.02)
+    reps, arr = _run(deck, tmp_path, 2)
+    _check_balance(reps)
+    assert reps[0]["gpu"]["n_transported"] > 1.0e7
+    # the deterministic mode sees the same photons (identical integer bookkeeping) and the same tallies to rounding
+    reps_d, arr_d = _run(deck, tmp_path, 1, tally_mode=gpu.TALLY_DETERMINISTIC)
+    for k in ("n_transported", "n_census", "n_killed", "n_exit", "n_events", "n_scatters", "n_crossings",
+              "n_reflections", "n_deposits"):
+        assert reps[0]["gpu"][k] == reps_d[0]["gpu"][k], k
+    s = arr_d[0][0].max()
+    assert np.max(np.abs(arr[0][0] - arr_d[0][0])) <= 1e-9 * s
+    assert abs(reps[0]["gpu"]["census_E"] - reps_d[0]["gpu"]["census_E"]) <= 1e-12 * reps[0]["pre_census_E"]
+
+
+def test_hot_zone_full_size(tmp_path):
+    # configs[1]: 200 x 200 x 1 cells, gray, 1e6 photons (reference inputs/hot_zone_input.xml)
+    reps, _ = _run(decks.hot_zone(t_stop=0.05), tmp_path, 5)
+    _check_balance(reps)
+
+
+def test_marshak_wave_full_size(tmp_path):
+    # configs[0]: 25 cells, T-dependent opacity, SOURCE face, 1e6 photons
+    reps, _ = _run(decks.marshak_wave(t_stop=0.05), tmp_path, 5)
+    _check_balance(reps)
+    assert all(r["source_E"] > 0 for r in reps)
+
+
+def test_big_cube_scaled(tmp_path):
+    # configs[4] scaled to one GPU: 200^3 cells, 2e7 photons per cycle
+    reps, _ = _run(decks.big_cube(n=200, photons=20_000_000, t_stop=0.002), tmp_path, 2)
+    _check_balance(reps)
