@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- photon histories/sec of the replicated IMC cycle on the 30-group 3-D hohlraum (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
+
+A "step" is one IMC cycle = one pass of the hot path (source -> transport -> census/tally) over that cycle's photons.
+Workload at N = 1: BASELINE.json configs[2], `3D_hohlraum_single_node` (65x65x140 cells, 30 groups, 1e7 user photons
+per cycle); at N > 1 the same deck with 1e7 x N user photons, rank r playing replicated-mode rank r ("weak" scaling:
+per-GPU photons fixed) and one in-place NCCL all-reduce of the packed tally buffer per cycle.  Synthetic problem: the
+deck is generated (branson_b200/decks.py) from the reference deck's numbers; all randomness is Threefry(seed, stream).
+
+JSON line (rank 0):
+  value     whole-job histories/s over the K timed cycles, device-resident (CUDA events on the ctx stream around
+            source + transport + census of every cycle; max over ranks)
+  e2e       the same K cycles timed by wall clock through the public cycle API with HOST buffers: host physics
+            (calculate_photon_energy / update_temperature), H2D of f/op_a/op_s and the source energies, the device
+            work, the tally all-reduce and the D2H of the tallies
+  roofline  the history-transport kernel: algorithmic bytes (counted exactly by the kernel)
+            / its CUDA-event time, against the measured HBM copy bandwidth
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/branson_ref_g30, OpenMP on all host cores) on a bounded
+            sample of the same workload (N = 1, rank 0 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_GROUPS = 30
+PHOTONS_PER_GPU = 10_000_000
+DT = 0.01
+METRIC = "photon histories/sec (3D hohlraum, 30 groups, replicated)"
+UNIT = "histories/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def make_deck(n_gpus: int, cycles: int, photons_per_gpu: int = PHOTONS_PER_GPU, threads: int = 1):
+    from branson_b200 import decks
+    d = decks.hohlraum_single(photons=photons_per_gpu * n_gpus, t_stop=DT * cycles)
+    return d.with_(n_omp_threads=threads, dd_transport_type="REPLICATED")
+
+
+def config_dict(n_gpus: int, photons_per_gpu: int):
+    return {"workload": "3D_hohlraum_single_node (BASELINE configs[2]): 65x65x140 cells, N_GROUPS=30, REPLICATED, "
+                        f"{photons_per_gpu:.0e} user photons per cycle per GPU, dt=0.01, HISTORY algorithm, atomic tallies",
+            "photons_per_cycle": photons_per_gpu * n_gpus, "n_cells": 591500, "n_groups": N_GROUPS,
+            "parallelism": f"replicated x{n_gpus} (photons partitioned, one tally all-reduce per cycle)",
+            "l2": "inputs larger than L2 (>= 1 GB of photon state per GPU and cycle; no explicit flush)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref; the oracle port if the reference binary is absent)
+# ----------------------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_cpu(cycles: int, photons: int, threads: int, timeout: float = 1500.0):
+    """Runs the unmodified reference binary on a reduced-photon copy of the bench deck.  Returns per-cycle
+    (photons transported, transport seconds, source seconds) parsed from its own report, and the kind."""
+    from oracle import refio
+    deck = make_deck(1, cycles, photons_per_gpu=photons, threads=threads)
+    exe = refio.stock_binary_path(N_GROUPS)
+    if os.path.exists(exe):
+        tmp = tempfile.mkdtemp(prefix="branson_cpu_")
+        xml = deck.write(os.path.join(tmp, "deck.xml"))
+        env = dict(os.environ, BRANSON_SHIM_NRANKS="1", OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        res = subprocess.run([exe, xml], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             timeout=timeout)
+        wall = time.time() - t0
+        if res.returncode != 0:
+            raise RuntimeError("reference binary failed:\n" + res.stdout[-2000:])
+        n = [int(x) for x in re.findall(r"Total Photons transported: (\d+)", res.stdout)]
+        t = [float(x) for x in re.findall(r"Transport time max/min: ([0-9.eE+-]+)/", res.stdout)]
+        s = [float(x) for x in re.findall(r"source time: ([0-9.eE+-]+)", res.stdout)]
+        assert len(n) == len(t) == cycles, res.stdout[-2000:]
+        return {"kind": "reference", "cores": threads, "photons": n, "transport_s": t, "source_s": s, "wall_s": wall}
+    # fallback: the plain-C restatement (scalar, one core)
+    from oracle import port
+    sim = port.OracleSim(deck)
+    n, t = [], []
+    t0 = time.time()
+    for _ in range(cycles):
+        sim.cycle(keep_photons=False)
+        n.append(int(sim.get("n_photons")[0]))
+        t.append(sim.transport_seconds())
+    return {"kind": "port", "cores": 1, "photons": n, "transport_s": t, "source_s": [0.0] * cycles,
+            "wall_s": time.time() - t0}
+
+
+def cpu_baseline_block(sample_photons: int, cycles: int = 3):
+    threads = host_cores()
+    r = run_reference_cpu(cycles, sample_photons, threads)
+    # cycle 1 is the streaming transient (no scattering yet); quote the later cycles, like the timed GPU cycles
+    hist = sum(r["photons"][1:])
+    secs = sum(r["transport_s"][1:])
+    return {"value": hist / secs, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+            "sample": f"same deck with {sample_photons} user photons per cycle, {cycles} cycles, cycles 2-{cycles} quoted "
+                      f"({hist} histories in {secs:.2f} s of the reference's own 'Transport time'; serial sourcing "
+                      f"{sum(r['source_s'][1:]):.2f} s extra; whole run {r['wall_s']:.1f} s)"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = host_cores()
+    sample = args.ref_photons
+    cycles = args.warmup + args.steps
+    r = run_reference_cpu(cycles, sample, threads)
+    hist = sum(r["photons"][args.warmup:])
+    t_tr = sum(r["transport_s"][args.warmup:])
+    t_all = t_tr + sum(r["source_s"][args.warmup:])
+    line = {"impl": "reference", "metric": METRIC, "value": hist / t_tr, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tr / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.gpus, PHOTONS_PER_GPU),
+            "cpu_baseline": {"value": hist / t_tr, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                             "sample": f"each step = one cycle of the same deck at {sample} user photons "
+                                       f"(bounded sample of the 1e7-photon workload); transport time as the reference "
+                                       f"reports it"},
+            "e2e": {"value": hist / t_all, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(g: dict) -> float:
+    """DESIGN.md section 5 / BASELINE.md section 4: bytes one launch of the transport kernel must move."""
+    n_hist, n_visit = g["n_transported"], g["n_transported"] + g["n_crossings"]
+    return (n_hist * (96 + 9) + n_visit * 8 + g["n_group_lookups"] * 16 + g["n_deposits"] * 32 + g["n_census"] * 96)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if k in j:
+                    return float(j[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the transport kernel from the committed ncu capture of this workload, else None."""
+    p = os.path.join(ROOT, "profiles", "transport_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def our_arm(args):
+    import torch
+
+    from branson_b200 import driver, gpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # the driver launches N > 1 through torchrun; a bare call re-executes itself that way
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        comm = driver.TorchComm(f"cuda:{local}")
+
+    cycles = args.warmup + args.steps
+    deck = make_deck(world, cycles, photons_per_gpu=args.photons)
+    tmp = tempfile.mkdtemp(prefix="branson_bench_")
+    xml = deck.write(os.path.join(tmp, f"deck_rank{rank}.xml"))
+    d = driver.Driver(xml, n_groups=N_GROUPS, rank=rank, n_ranks=world, device=local,
+                      algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, comm=comm)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        d.cycle()
+    launches_before = d.gpu_context().stats()["n_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    t0 = time.perf_counter()
+    reps = [d.cycle() for _ in range(args.steps)]
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    g = [r["gpu"] for r in reps]
+    dev_ms = sum(x["ms_source"] + x["ms_transport"] + x["ms_census"] for x in g)
+    tr_ms = sum(x["ms_transport"] for x in g)
+    hist = sum(x["n_transported"] for x in g)
+    abytes = sum(algorithmic_bytes(x) for x in g)
+    launches = g[-1]["n_launches"] - launches_before  # kernels launched through the ctx inside the timed region
+    vals = torch.tensor([dev_ms, wall, tr_ms, float(hist), float(abytes)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        mx = vals.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        sm = vals.clone()
+        torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM)
+        dev_ms_max, wall_max, tr_ms_max = mx[0].item(), mx[1].item(), mx[2].item()
+        hist_all = sm[3].item()
+    else:
+        dev_ms_max, wall_max, tr_ms_max, hist_all = dev_ms, wall, tr_ms, float(hist)
+
+    if rank == 0:
+        n_cells = int(d.param("n_cells"))
+        peak, peak_src = measured_peak()
+        achieved = abytes / (tr_ms * 1e-3) / 1e9  # rank 0's kernel: bytes per launch / its average duration
+        h2d = 5 * n_cells * 8  # f, op_a, op_s, E_emission, E_source
+        d2h = 2 * n_cells * 8 + 256
+        line = {"metric": METRIC, "value": hist_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(world, args.photons),
+                "e2e": {"value": hist_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * wall_max / args.steps,
+                        "host_phase_ms_per_step": {k[2:]: 1e3 * sum(r[k] for r in reps) / args.steps for k in
+                                                   ("t_calc_energy", "t_cell_upload", "t_source", "t_transport",
+                                                    "t_allreduce", "t_tally_download", "t_update_T")}},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "k_transport_history", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "traffic": ncu_traffic(),
+                             "algorithmic_bytes_per_launch": abytes / args.steps,
+                             "bytes_per_history": abytes / hist, "kernel_ms_per_launch": tr_ms / args.steps,
+                             "kernel_histories_per_s": hist / (tr_ms * 1e-3),
+                             "events_per_history": sum(x["n_events"] for x in g) / hist,
+                             "scatters_per_history": sum(x["n_scatters"] for x in g) / hist,
+                             "note": "scattering-dominated cycles are INT32/FP64-pipe bound (Threefry + log/exp/sincos), "
+                                     "see DESIGN.md section 5 and profiles/"},
+                "clocks": clocks,
+                "conservation": {"max_rel_radiation_balance": max(
+                    abs(r["rad_balance_exact"]) / (r["pre_census_E"] + r["emission_E"] + r["source_E"]) for r in reps)}}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_block(args.cpu_sample_photons)
+            except Exception as e:  # the bench line must still be printed
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    d.close()
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local])
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--photons", type=int, default=PHOTONS_PER_GPU, help="user photons per cycle per GPU")
+    ap.add_argument("--algorithm", default="history", choices=["history", "event"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-photons", type=int, default=1_000_000)
+    ap.add_argument("--ref-photons", type=int, default=400_000,
+                    help="--impl reference: user photons per cycle of the bounded sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return our_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -80,8 +80,9 @@ struct bgpu_ctx {
   int blocks_per_sm = 0;  // 0: occupancy query
   uint32_t chunk = 128;
 
+  uint64_t launches = 0;  // kernels launched through this ctx since creation
   bgpu_cycle_stats stats{};
-  double pre_census_E = 0.0;
+  double pre_census_E = 0.0, new_photon_E = 0.0;
   bool stats_valid = false;
 };
 
@@ -203,13 +204,13 @@ __global__ void k_copy_soa(PhotonSoA src, uint64_t src_off, PhotonSoA dst, uint6
 
 // in-order (tile-tree) sum of E over a photon list: get_photon_list_E (src/census_functions.h:31-46)
 __global__ void __launch_bounds__(CT_THREADS) k_list_E_tiles(const double2 *__restrict__ ee, uint64_t n,
-                                                             double *__restrict__ tile_E) {
+                                                             double *__restrict__ tile_E, int use_E0) {
   __shared__ double s_red[CT_THREADS >> 5];
   const uint64_t base = (uint64_t)blockIdx.x * CT_TILE + (uint64_t)threadIdx.x * CT_ITEMS;
   double e = 0.0;
 #pragma unroll
   for (int i = 0; i < CT_ITEMS; ++i)
-    if (base + i < n) e += ee[base + i].x;
+    if (base + i < n) e += use_E0 ? ee[base + i].y : ee[base + i].x;
   const double b = block_sum(e, s_red);
   if (threadIdx.x == 0) tile_E[blockIdx.x] = b;
 }
@@ -292,8 +293,11 @@ int device_scan(bgpu_ctx *c, const uint32_t *in, uint64_t n, uint64_t *out) {
   const uint32_t tiles = (uint32_t)((n + CT_TILE - 1) / CT_TILE);
   if (ensure(c, c->scr_tile_sum, 4ull * tiles)) return 1;
   if (ensure(c, c->scr_tile_off, 8ull * (tiles + 1))) return 1;
+  ++c->launches;
   k_scan_tile_sums<<<tiles, CT_THREADS, 0, c->stream>>>(in, n, (uint32_t *)c->scr_tile_sum.p);
+  ++c->launches;
   k_scan_single<<<1, 1024, 0, c->stream>>>((const uint32_t *)c->scr_tile_sum.p, tiles, (uint64_t *)c->scr_tile_off.p);
+  ++c->launches;
   k_scan_apply<<<tiles, CT_THREADS, 0, c->stream>>>(in, n, (const uint64_t *)c->scr_tile_off.p, out);
   CU(c, cudaGetLastError());
   return 0;
@@ -317,6 +321,7 @@ int launch_history(bgpu_ctx *c, const TransportParams &P) {
   uint64_t blocks = (uint64_t)c->n_sm * per_sm;
   const uint64_t max_useful = (P.n + c->block_threads - 1) / c->block_threads;
   if (blocks > max_useful) blocks = std::max<uint64_t>(max_useful, 1);
+  ++c->launches;
   kern<<<(unsigned)blocks, c->block_threads, use_smem ? smem : 0, c->stream>>>(P);
   CU(c, cudaGetLastError());
   return 0;
@@ -384,6 +389,7 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   if (ensure(c, c->scr_keys_out, 4 * n_dep)) return 1;
   if (ensure(c, c->scr_vals_in, 4 * n_dep)) return 1;
   if (ensure(c, c->scr_vals_out, 4 * n_dep)) return 1;
+  ++c->launches;
   k_iota<<<grid_for(n_dep, 256), 256, 0, c->stream>>>((uint32_t *)c->scr_vals_in.p, n_dep);
   int end_bit = 1;
   while ((1ull << end_bit) < c->mesh.n_cells) ++end_bit;
@@ -398,8 +404,10 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   if (ensure(c, c->scr_seg, 16ull * c->mesh.n_cells)) return 1;
   CU(c, cudaMemsetAsync(c->scr_seg.p, 0, 16ull * c->mesh.n_cells, c->stream));
   uint64_t *seg_start = (uint64_t *)c->scr_seg.p, *seg_end = seg_start + c->mesh.n_cells;
+  ++c->launches;
   k_seg_bounds<<<grid_for(n_dep, 256), 256, 0, c->stream>>>((const uint32_t *)c->scr_keys_out.p, n_dep, seg_start,
                                                              seg_end);
+  ++c->launches;
   k_seg_sum<<<grid_for(c->mesh.n_cells, 128), 128, 0, c->stream>>>(c->mesh.n_cells, seg_start, seg_end,
                                                                    (const uint32_t *)c->scr_vals_out.p,
                                                                    (const double2 *)c->scr_dep_val.p,
@@ -426,7 +434,9 @@ int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
     T.n_census = (uint32_t *)p;  p += 4ull * tiles;
     T.n_killed = (uint32_t *)p;  p += 4ull * tiles;
     T.n_exit = (uint32_t *)p;
+    ++c->launches;
     k_census_tiles<<<tiles, CT_THREADS, 0, c->stream>>>(c->d_desc, c->work.ee, n, T);
+    ++c->launches;
     k_scan_partials<<<1, 1024, 0, c->stream>>>(tiles, T, c->d_results, c->d_stats);
     CU(c, cudaGetLastError());
     CU(c, cudaMemcpyAsync(st, c->d_stats, 8 * ST_COUNT, cudaMemcpyDeviceToHost, c->stream));
@@ -435,6 +445,7 @@ int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
     const uint64_t nc = st[ST_N_CENSUS];
     if (ensure_soa(c, c->census, nc, 0)) return 1;
     if (nc) {
+      ++c->launches;
       k_census_scatter<<<tiles, CT_THREADS, 0, c->stream>>>(c->d_desc, c->work, n, c->census, 0, T.tile_off,
                                                             K_C * next_dt);
       CU(c, cudaGetLastError());
@@ -469,16 +480,19 @@ int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
   s.n_reflections = st[ST_REFLECTIONS];
   s.n_deposits = st[ST_DEPOSITS];
   s.n_group_lookups = st[ST_LOOKUPS];
+  s.n_launches = c->launches;
   return 0;
 }
 
-int list_energy(bgpu_ctx *c, const PhotonSoA &list, uint64_t off, uint64_t n, double *out) {
+int list_energy(bgpu_ctx *c, const PhotonSoA &list, uint64_t off, uint64_t n, double *out, int use_E0 = 0) {
   *out = 0.0;
   if (!n) return 0;
   const uint32_t tiles = (uint32_t)((n + CT_TILE - 1) / CT_TILE);
   if (ensure(c, c->scr_tile_sum, 8ull * tiles + 8)) return 1;
   double *tile_E = (double *)c->scr_tile_sum.p;
-  k_list_E_tiles<<<tiles, CT_THREADS, 0, c->stream>>>(list.ee + off, n, tile_E);
+  ++c->launches;
+  k_list_E_tiles<<<tiles, CT_THREADS, 0, c->stream>>>(list.ee + off, n, tile_E, use_E0);
+  ++c->launches;
   k_sum_serial<<<1, 32, 0, c->stream>>>(tile_E, tiles, c->d_results + 2);
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(out, c->d_results + 2, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -600,6 +614,7 @@ int bgpu_set_cell_data(bgpu_ctx *c, const double *f, const double *op_a, const d
   CU(c, cudaMemcpyAsync(c->d_f, f, 8 * nc, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(c->d_cell_stage, op_a, 8 * nc, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(c->d_cell_stage + nc, op_s, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  ++c->launches;
   k_expand_groups<<<grid_for(nc * c->mesh.G, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_cell_stage,
                                                                         c->d_cell_stage + nc, c->d_opa, c->d_ops);
   CU(c, cudaGetLastError());
@@ -625,20 +640,22 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
   if (!c || !E_emission || !E_source) return fail(c, "bgpu_source: null argument");
   CU(c, cudaSetDevice(c->device));
   const uint32_t nc = c->mesh.n_cells;
-  CU(c, cudaEventRecord(c->ev[0], c->stream));
   double *dE = c->d_cell_stage;
   CU(c, cudaMemcpyAsync(dE, E_emission, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(dE + nc, E_source, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
   if (E_census) CU(c, cudaMemcpyAsync(dE + 2ull * nc, E_census, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->ev[0], c->stream));  // inputs are resident from here on
   if (ensure(c, c->scr_counts, 4ull * 3 * nc)) return 1;
   if (ensure(c, c->scr_offsets, 8ull * (3ull * nc + 2))) return 1;
   uint32_t *cnt2 = (uint32_t *)c->scr_counts.p, *cnt1 = cnt2 + 2ull * nc;
   uint64_t *off2 = (uint64_t *)c->scr_offsets.p, *off1 = off2 + 2ull * nc + 1;
+  ++c->launches;
   k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 2, dE, dE + nc, c->n_user, total_E, cnt2);
   if (device_scan(c, cnt2, 2ull * nc, off2)) return 1;
   uint64_t n_new = 0, n_init = 0;
   CU(c, cudaMemcpyAsync(&n_new, off2 + 2ull * nc, 8, cudaMemcpyDeviceToHost, c->stream));
   if (E_census) {
+    ++c->launches;
     k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 1, dE + 2ull * nc, nullptr, c->n_user, total_E, cnt1);
     if (device_scan(c, cnt1, nc, off1)) return 1;
     CU(c, cudaMemcpyAsync(&n_init, off1 + nc, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -664,6 +681,7 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
     S.E1 = dE + nc;
     // src/source.h:221-222
     S.stream_base = 10000000000000ULL * (uint64_t)cycle + c->n_user * (uint64_t)c->rank;
+    ++c->launches;
     k_source_sample<<<grid_for(n_new, 256), 256, 0, c->stream>>>(S);
   }
   if (E_census) {
@@ -676,10 +694,12 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
       S.E0 = dE + 2ull * nc;
       S.E1 = nullptr;
       S.stream_base = c->n_user * (uint64_t)c->rank;  // src/source.h:144
+      ++c->launches;
       k_source_sample<<<grid_for(n_init, 256), 256, 0, c->stream>>>(S);
     }
   } else if (n_cen) {
     // join_photon_arrays: all = [new ..., census ...] (src/census_functions.h:21-29)
+    ++c->launches;
     k_copy_soa<<<grid_for(n_cen, 256), 256, 0, c->stream>>>(c->census, 0, c->work, n_new, n_cen);
   }
   CU(c, cudaGetLastError());
@@ -687,10 +707,12 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
   c->n_work = n_total;
   // pre-transport census energy, get_photon_list_E (src/replicated_driver.h:61,71)
   if (list_energy(c, c->work, n_new, n_cen, &c->pre_census_E)) return 1;
+  if (list_energy(c, c->work, 0, n_new, &c->new_photon_E, 1)) return 1;
   CU(c, cudaEventRecord(c->ev[1], c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   c->stats = bgpu_cycle_stats{};
   c->stats.pre_census_E = c->pre_census_E;
+  c->stats.new_photon_E = c->new_photon_E;
   c->stats.n_new = n_new;
   c->stats.n_transported = n_total;
   CU(c, cudaEventElapsedTime(&c->stats.ms_source, c->ev[0], c->ev[1]));
@@ -710,6 +732,7 @@ int bgpu_transport(bgpu_ctx *c, double next_dt, int algorithm, int tally_mode) {
   CU(c, cudaEventRecord(c->ev[4], c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   c->stats.pre_census_E = c->pre_census_E;
+  c->stats.new_photon_E = c->new_photon_E;
   c->stats.n_new = c->n_new;
   c->stats.n_transported = c->n_work;
   CU(c, cudaEventElapsedTime(&c->stats.ms_transport, c->ev[2], c->ev[3]));
@@ -733,6 +756,7 @@ int bgpu_get_tallies(bgpu_ctx *c, double *abs_E, double *track_E, bgpu_cycle_sta
     if (track_E)
       for (uint64_t i = 0; i < nc; ++i) track_E[i] = h[2 * i + 1];
   }
+  c->stats.n_launches = c->launches;
   if (stats) *stats = c->stats;
   return 0;
 }
@@ -779,6 +803,7 @@ int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cel
   c->n_new = n;
   if (n) {
     CU(c, cudaMemcpyAsync(c->scr_aos.p, photons, 120 * n, cudaMemcpyHostToDevice, c->stream));
+    ++c->launches;
     k_aos_to_soa<<<grid_for(n, 128), 128, 0, c->stream>>>((const uint64_t *)c->scr_aos.p, n, c->work, c->ctr_hi,
                                                           c->d_stats);
     unsigned long long bad = 0;
@@ -788,6 +813,7 @@ int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cel
       return fail(c, "bgpu_transport_photons_aos: %llu photons carry an RNG seed/spawn word different from the ctx seed",
                   bad);
     if (run_transport(c, algorithm, tally_mode, true)) return 1;
+    ++c->launches;
     k_soa_to_aos<<<grid_for(n, 128), 128, 0, c->stream>>>((uint64_t *)c->scr_aos.p, n, c->work, c->d_desc);
     CU(c, cudaGetLastError());
     CU(c, cudaMemcpyAsync(photons, c->scr_aos.p, 120 * n, cudaMemcpyDeviceToHost, c->stream));

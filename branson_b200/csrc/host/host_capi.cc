@@ -111,6 +111,7 @@ int bhost_cycle(bhost_driver *d, bhost_cycle_report *out) {
       o.pre_census_E = s.g_pre_census_E; o.post_census_E = s.g_post_census_E; o.pre_mat_E = s.g_pre_mat_E;
       o.post_mat_E = s.g_post_mat_E; o.exit_E = s.g_exit_E;
       o.rad_conservation = s.rad_conservation; o.mat_conservation = s.mat_conservation;
+      o.rad_balance_exact = r.rad_balance_exact;
       o.trans_particles = s.g_trans_particles; o.census_size = s.g_census_size;
       *out = o;
     }

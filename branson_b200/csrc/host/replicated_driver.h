@@ -12,6 +12,7 @@
 //   rank != 0 zeroes its material sums, print_conservation, next_time_step (:100-120)
 #pragma once
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <iostream>
 #include <vector>
@@ -30,6 +31,7 @@ struct Cycle_Report {
   bgpu_cycle_stats gpu;  // this rank's device statistics
   // wall-clock seconds of the host-visible phases of this cycle
   double t_calc_energy, t_cell_upload, t_source, t_transport, t_allreduce, t_tally_download, t_update_T, t_cycle;
+  double rad_balance_exact;
 };
 
 struct Driver_Options {
@@ -131,6 +133,21 @@ public:
                          opt.tally_mode, rep);
 
     const double t4 = wall_now();
+    {
+      // Radiation balance from what the device made and tallied, with a compensated (Neumaier) sum over cells.  The
+      // reference's own residual (IMC_State::print_conservation) adds abs_E serially in cell order
+      // (src/mesh.h:359): with ~6e5 cells, addends below half an ulp of the running sum are dropped, which alone is
+      // a relative 1e-12 (tools/debug_conservation.py) although the photons conserve energy exactly.
+      double sum = 0.0, comp = 0.0;
+      for (double v : abs_E) {
+        const double t = sum + v;
+        comp += (std::abs(sum) >= std::abs(v)) ? (sum - t) + v : (v - t) + sum;
+        sum = t;
+      }
+      double rank_part = rep.gpu.census_E + rep.gpu.exit_E - rep.gpu.pre_census_E - st.new_photon_E;
+      comm.sum(&rank_part, 1);
+      rep.rad_balance_exact = (sum + comp) + rank_part;
+    }
     last_abs_E = abs_E;
     last_track_E = track_E;
     mesh.update_temperature(abs_E, track_E, imc_state);

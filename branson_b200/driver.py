@@ -46,7 +46,7 @@ class CycleReport(C.Structure):
                 ("absorbed_E", C.c_double), ("emission_E", C.c_double), ("source_E", C.c_double),
                 ("pre_census_E", C.c_double), ("post_census_E", C.c_double), ("pre_mat_E", C.c_double),
                 ("post_mat_E", C.c_double), ("exit_E", C.c_double), ("rad_conservation", C.c_double),
-                ("mat_conservation", C.c_double), ("trans_particles", C.c_uint64), ("census_size", C.c_uint64)]
+                ("mat_conservation", C.c_double), ("rad_balance_exact", C.c_double), ("trans_particles", C.c_uint64), ("census_size", C.c_uint64)]
 
     def as_dict(self):
         d = {}

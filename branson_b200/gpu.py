@@ -30,10 +30,12 @@ class MeshDesc(C.Structure):
 
 class CycleStats(C.Structure):
     _fields_ = [("census_E", C.c_double), ("exit_E", C.c_double), ("pre_census_E", C.c_double),
+                ("new_photon_E", C.c_double),
                 ("n_new", C.c_uint64), ("n_transported", C.c_uint64), ("n_census", C.c_uint64),
                 ("n_killed", C.c_uint64), ("n_exit", C.c_uint64), ("n_events", C.c_uint64),
                 ("n_scatters", C.c_uint64), ("n_crossings", C.c_uint64), ("n_reflections", C.c_uint64),
-                ("n_deposits", C.c_uint64), ("n_group_lookups", C.c_uint64), ("ms_source", C.c_float),
+                ("n_deposits", C.c_uint64), ("n_group_lookups", C.c_uint64), ("n_launches", C.c_uint64),
+                ("ms_source", C.c_float),
                 ("ms_transport", C.c_float), ("ms_census", C.c_float), ("ms_total", C.c_float)]
 
     def as_dict(self):

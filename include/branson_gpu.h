@@ -75,12 +75,14 @@ typedef struct {
   double census_E;      /* post-transport census energy */
   double exit_E;
   double pre_census_E;  /* get_photon_list_E of the census entering this cycle */
+  double new_photon_E;  /* sum of E0 over the photons make_photons created this cycle (exact-balance diagnostic) */
   uint64_t n_new;       /* photons created by make_photons this cycle */
   uint64_t n_transported; /* all_photons.size() */
   uint64_t n_census;    /* census_list.size() after transport */
   uint64_t n_killed, n_exit;
   /* exact event counts of the cycle (for the algorithmic-bytes roofline) */
   uint64_t n_events, n_scatters, n_crossings, n_reflections, n_deposits, n_group_lookups;
+  uint64_t n_launches; /* kernels launched through this ctx since bgpu_create (cumulative) */
   /* device times (CUDA events on the ctx stream), milliseconds */
   float ms_source, ms_transport, ms_census, ms_total;
 } bgpu_cycle_stats;

@@ -53,6 +53,9 @@ typedef struct {
   /* IMC_State after print_conservation (global sums) */
   double absorbed_E, emission_E, source_E, pre_census_E, post_census_E, pre_mat_E, post_mat_E, exit_E;
   double rad_conservation, mat_conservation;
+  /* the same radiation balance from compensated sums of what the device actually made and tallied (see
+   * Replicated_Driver::cycle): independent of the serial cell-order sum the reference formula uses */
+  double rad_balance_exact;
   uint64_t trans_particles, census_size;
 } bhost_cycle_report;
 

@@ -64,6 +64,7 @@ def test_driver_cycles_match_oracle(name, tmp_path):
             assert abs(rep[k] - sim.get(k)[0]) <= 1e-9 * max(e, abs(sim.get(k)[0])), k
         total = rep["pre_census_E"] + rep["emission_E"] + rep["source_E"]
         assert abs(rep["rad_conservation"]) <= 1e-12 * total, (rep["rad_conservation"], total)
+        assert abs(rep["rad_balance_exact"]) <= 1e-12 * total, (rep["rad_balance_exact"], total)
         assert abs(rep["mat_conservation"]) <= 1e-12 * max(abs(rep["pre_mat_E"]), abs(rep["post_mat_E"]))
     assert d.finished() and cyc == deck.n_cycles()
 
