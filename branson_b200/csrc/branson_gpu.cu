@@ -79,6 +79,8 @@ struct bgpu_ctx {
   int block_threads = 128;
   int blocks_per_sm = 0;  // 0: occupancy query
   uint32_t chunk = 128;
+  uint64_t event_tail = 0;   // active-list size below which BGPU_EVENT hands over to the history kernel (0: auto)
+  uint32_t event_passes = 0;
 
   uint64_t launches = 0;  // kernels launched through this ctx since creation
   bgpu_cycle_stats stats{};
@@ -303,14 +305,14 @@ int device_scan(bgpu_ctx *c, const uint32_t *in, uint64_t n, uint64_t *out) {
   return 0;
 }
 
-template <int MODE>
+template <int MODE, bool RESUME = false>
 int launch_history(bgpu_ctx *c, const TransportParams &P) {
   const size_t smem = (size_t)P.mesh.n_faces * 8;
   const bool use_smem = smem <= 160 * 1024;
   const bool ctrs = P.counters != nullptr;
   void (*kern)(const TransportParams) = nullptr;
-  if (use_smem) kern = ctrs ? k_transport_history<MODE, true, true> : k_transport_history<MODE, false, true>;
-  else kern = ctrs ? k_transport_history<MODE, true, false> : k_transport_history<MODE, false, false>;
+  if (use_smem) kern = ctrs ? k_transport_history<MODE, true, true, RESUME> : k_transport_history<MODE, false, true, RESUME>;
+  else kern = ctrs ? k_transport_history<MODE, true, false, RESUME> : k_transport_history<MODE, false, false, RESUME>;
   if (use_smem && smem > 48 * 1024)
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = c->blocks_per_sm;
@@ -324,6 +326,71 @@ int launch_history(bgpu_ctx *c, const TransportParams &P) {
   ++c->launches;
   kern<<<(unsigned)blocks, c->block_threads, use_smem ? smem : 0, c->stream>>>(P);
   CU(c, cudaGetLastError());
+  return 0;
+}
+
+// BGPU_EVENT: lockstep passes regrouped at scatters (event.cuh), tail finished by the history kernel in RESUME mode
+int run_event(bgpu_ctx *c, TransportParams P) {
+  const uint64_t n = P.n;
+  const size_t bytes = 16 * n + 16 * n + 4 * n + 4 * n + 4 * n + 64;
+  if (ensure(c, c->scr_event, bytes)) return 1;
+  char *p = (char *)c->scr_event.p;
+  double2 *acc = (double2 *)p;                 p += 16 * n;
+  uint4 *cnt = (uint4 *)p;                     p += 16 * n;
+  uint32_t *lk = (uint32_t *)p;                p += 4 * n;
+  uint32_t *list_a = (uint32_t *)p;            p += 4 * n;
+  uint32_t *list_b = (uint32_t *)p;            p += 4 * n;
+  unsigned long long *n_out = (unsigned long long *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  const size_t smem = (size_t)P.mesh.n_faces * 8;
+  const bool use_smem = smem <= 160 * 1024;
+  const bool ctrs = P.counters != nullptr;
+  void (*kern)(const EventParams) = nullptr;
+  if (use_smem) kern = ctrs ? k_event_pass<true, true> : k_event_pass<false, true>;
+  else kern = ctrs ? k_event_pass<true, false> : k_event_pass<false, false>;
+  if (use_smem && smem > 48 * 1024)
+    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, use_smem ? smem : 0));
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t machine = (uint64_t)c->n_sm * per_sm * 128;  // lanes resident at once
+  const uint64_t tail = c->event_tail ? c->event_tail : 2 * machine;
+  EventParams E{};
+  E.T = P;
+  E.acc = acc; E.cnt = cnt; E.lk = lk;
+  E.n_out = n_out;
+  uint64_t n_active = n;
+  const uint32_t *list_in = nullptr;
+  uint32_t *list_out = list_a;
+  bool first = true;
+  c->event_passes = 0;
+  while (n_active > 0) {
+    if (!first && n_active <= tail) {
+      TransportParams R = P;
+      R.n = n_active;
+      R.index_list = list_in;
+      R.carry_acc = acc; R.carry_cnt = cnt; R.carry_lk = lk;
+      CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
+      if (launch_history<TM_ATOMIC, true>(c, R)) return 1;
+      break;
+    }
+    CU(c, cudaMemsetAsync(n_out, 0, 8, c->stream));
+    E.list_in = list_in;
+    E.n_in = n_active;
+    E.list_out = list_out;
+    E.first = first ? 1 : 0;
+    uint64_t blocks = std::min<uint64_t>((n_active + 127) / 128, (uint64_t)c->n_sm * per_sm * 4);
+    ++c->launches;
+    kern<<<(unsigned)blocks, 128, use_smem ? smem : 0, c->stream>>>(E);
+    CU(c, cudaGetLastError());
+    unsigned long long h = 0;
+    CU(c, cudaMemcpyAsync(&h, n_out, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    n_active = h;
+    list_in = list_out;
+    list_out = (list_out == list_a) ? list_b : list_a;
+    first = false;
+    ++c->event_passes;
+  }
   return 0;
 }
 
@@ -357,9 +424,7 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   TransportParams P = make_params(c, writeback_all);
   if (algorithm == BGPU_EVENT) {
     if (tally_mode != BGPU_TALLY_ATOMIC) return fail(c, "the event-based variant supports BGPU_TALLY_ATOMIC only");
-    return run_event_transport(c->stream, P, c->n_sm, c->scr_event.p, c->scr_event.bytes,
-                               [&](size_t bytes) { return ensure(c, c->scr_event, bytes) ? (void *)nullptr : c->scr_event.p; },
-                               c->err);
+    return run_event(c, P);
   }
   if (tally_mode == BGPU_TALLY_ATOMIC) {
     CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
@@ -843,6 +908,12 @@ int bgpu_set_launch(bgpu_ctx *c, int block_threads, int blocks_per_sm, int chunk
   }
   c->blocks_per_sm = blocks_per_sm;
   if (chunk > 0) c->chunk = (uint32_t)chunk;
+  return 0;
+}
+
+int bgpu_set_event_tail(bgpu_ctx *c, uint64_t n_active) {
+  if (!c) return 1;
+  c->event_tail = n_active;
   return 0;
 }
 

@@ -1,4 +1,22 @@
-// event.cuh -- event-based transport variant (placeholder until the regrouped kernels land).
+// event.cuh -- event-based transport variant (BGPU_EVENT).
+//
+// The reference's event_based_transport.h (CPU only, :341-427) regroups the history loop by event type over an active
+// list so that each loop is uniform work.  The idea maps to the GPU as warp-divergence control: the expensive event is
+// the (effective) scatter -- 4 of the ~5 Threefry draws of an event, sincos, sqrt and the sequential group walk -- so
+// the photons are regrouped at scatters:
+//
+//   pass k:   for every photon of the active list, in lockstep:   [sample the scatter parked by pass k-1]
+//             then advance (distance sampling, implicit capture, cell crossings, reflections) until the history ends or
+//             the next scatter is reached; survivors park there and are appended to the next active list.
+//
+// Every lane of a warp therefore executes the scatter code together (100% lane efficiency in that phase), the kernel
+// carries no refill logic, and photon state streams through HBM once per scatter (coalesced 128-bit streams + 40 bytes
+// of carried thread-local tallies and counters).  When the active list no longer fills the machine the remaining
+// histories are finished by the persistent history kernel in RESUME mode.
+//
+// Per-photon results are identical to the HISTORY variant by construction (the same advance_event / scatter_event
+// device functions run in the same per-photon order; only the tally summation order differs) -- unlike the reference,
+// whose EVENT path is not photon-identical to its HISTORY path (note E).
 #pragma once
 #include <string>
 
@@ -6,10 +24,106 @@
 
 namespace bg {
 
-template <typename Alloc>
-int run_event_transport(cudaStream_t, const TransportParams &, int, void *, size_t, Alloc, std::string &err) {
-  err = "event-based transport variant is not built yet";
-  return 1;
+struct EventParams {
+  TransportParams T;
+  const uint32_t *list_in;   // nullptr on the first pass: identity
+  uint64_t n_in;
+  uint32_t *list_out;
+  unsigned long long *n_out;
+  double2 *acc;              // carried {loc_abs, loc_trk}
+  uint4 *cnt;                // carried counters
+  uint32_t *lk;
+  int first;
+};
+
+template <bool COUNTERS, bool SMEM>
+__global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
+  extern __shared__ double s_faces[];
+  __shared__ unsigned long long s_stats[6];
+  const TransportParams &P = E.T;
+  if (threadIdx.x < 6) s_stats[threadIdx.x] = 0ull;
+  const double *faces;
+  if (SMEM) {
+    for (uint32_t t = threadIdx.x; t < P.mesh.n_faces; t += blockDim.x) s_faces[t] = P.mesh.faces[t];
+    faces = s_faces;
+  } else {
+    faces = P.mesh.faces;
+  }
+  __syncthreads();
+  PCtx C;
+  C.fx = faces;
+  C.fy = faces + (P.mesh.nx + 1);
+  C.fz = C.fy + (P.mesh.ny + 1);
+  C.nx = P.mesh.nx; C.ny = P.mesh.ny; C.nz = P.mesh.nz; C.G = P.mesh.G;
+  C.sxy = C.nx * C.ny;
+  C.f = P.f; C.opa = P.opa; C.ops = P.ops;
+  C.ctr_hi = P.ctr_hi;
+  const unsigned lane_id = threadIdx.x & 31u;
+
+  auto deposit = [&](uint32_t cell, double a, double t) {
+    atomicAdd(&P.tally[cell].x, a);
+    atomicAdd(&P.tally[cell].y, t);
+  };
+
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t n_round = (E.n_in + 31) & ~31ull;  // whole warps stay converged for the ballots below
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+    const bool valid = t < E.n_in;
+    bool survivor = false;
+    uint64_t idx = 0;
+    if (valid) {
+      idx = E.list_in ? (uint64_t)E.list_in[t] : t;
+      PState S;
+      S.surface = 0;
+      pstate_load(S, P.ph, idx, C);
+      if (!E.first) {
+        const double2 acc = E.acc[idx];
+        const uint4 cn = E.cnt[idx];
+        S.loc_abs = acc.x; S.loc_trk = acc.y;
+        S.c_ev = cn.x; S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
+        S.c_lk = E.lk[idx];
+        // the parked scatter: every lane of the warp is here together
+        S.f = __ldg(&C.f[S.cell]);
+        const uint64_t o = (uint64_t)S.cell * C.G + S.group;
+        S.sig_a = __ldg(&C.opa[o]);
+        S.sig_s = __ldg(&C.ops[o]);
+        S.need_f = false; S.need_xs = false;
+        S.gmask |= 1ull << (S.group & 63u);
+        scatter_event(S, C);
+      }
+      uint8_t descriptor = EV_PASS;
+      int r;
+      do {
+        r = advance_event(S, C, P.mesh.bc, deposit, descriptor);
+      } while (r == R_CONTINUE);
+      if (r == R_DONE) {
+        close_visit(S);
+        stats_add(s_stats, S);
+        P.desc[idx] = descriptor;
+        P.ph.ee[idx] = make_double2(S.E, S.E0);
+        if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
+        if (COUNTERS) reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
+      } else {  // parked at a scatter
+        close_visit(S);  // the lookup count restarts with the reload of the next pass
+        P.ph.ee[idx] = make_double2(S.E, S.E0);
+        pstate_store_full(S, P.ph, idx);
+        E.acc[idx] = make_double2(S.loc_abs, S.loc_trk);
+        E.cnt[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
+        E.lk[idx] = S.c_lk;
+        survivor = true;
+      }
+    }
+    // warp-aggregated append of the survivors to the next active list
+    const unsigned m = __ballot_sync(0xffffffffu, survivor);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane_id == (unsigned)(__ffs(m) - 1)) base = atomicAdd(E.n_out, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (survivor) E.list_out[base + __popc(m & ((1u << lane_id) - 1u))] = (uint32_t)idx;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 }  // namespace bg

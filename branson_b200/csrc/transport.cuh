@@ -43,75 +43,278 @@ struct TransportParams {
   uint32_t *dep_cell;
   double2 *dep_val;
   unsigned long long *stats;
+  // RESUME launches (the tail of the event-based variant, event.cuh)
+  const uint32_t *index_list;
+  const double2 *carry_acc;
+  const uint4 *carry_cnt;
+  const uint32_t *carry_lk;
 };
 
-struct Lane {
+// Photon state of one lane, kept in registers for the whole history.
+struct PState {
   double x, y, z, ax, ay, az, E, E0, life;
-  uint64_t ctr, stream, idx;
+  uint64_t ctr, stream;
   uint32_t cell, group;
   int i, j, k;
+  double f, sig_a, sig_s;        // cell / group data of the current visit
+  double loc_abs, loc_trk;       // thread-local tallies of the current cell visit (reference :45-46)
+  uint32_t surface;              // persists across events like the reference's surface_cross (:37)
+  uint32_t c_ev, c_sc, c_cr, c_rf, c_lk;  // per-photon counters: events, scatters, crossings, reflections, lookups
+  uint64_t gmask;                // groups touched during the current cell visit (algorithmic-bytes accounting)
+  bool need_f, need_xs;
 };
 
-template <bool SMEM>
-__device__ __forceinline__ double face_at(const double *faces, uint32_t idx) {
-  return faces[idx];
+struct PCtx {
+  const double *fx, *fy, *fz;    // per-axis faces (shared memory when they fit)
+  uint32_t nx, ny, nz, G, sxy;
+  const double *f, *opa, *ops;
+  uint64_t ctr_hi;
+};
+
+enum : int { R_CONTINUE = 0, R_DONE = 1, R_SCATTER = 2 };
+
+__device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint64_t idx, const PCtx &C) {
+  const double2 xy = ph.xy[idx], za = ph.za[idx], bc = ph.bc[idx], ee = ph.ee[idx];
+  const ulonglong2 lc = ph.lc[idx], sg = ph.sg[idx];
+  S.x = xy.x; S.y = xy.y; S.z = za.x; S.ax = za.y; S.ay = bc.x; S.az = bc.y;
+  S.E = ee.x; S.E0 = ee.y;
+  S.life = __longlong_as_double((long long)lc.x);
+  S.ctr = lc.y;
+  S.stream = sg.x;
+  S.cell = (uint32_t)sg.y;
+  S.group = (uint32_t)(sg.y >> 32);
+  const uint32_t kk = S.cell / C.sxy;
+  const uint32_t rem = S.cell - kk * C.sxy;
+  const uint32_t jj = rem / C.nx;
+  S.k = (int)kk; S.j = (int)jj; S.i = (int)(rem - jj * C.nx);
+  S.loc_abs = 0.0; S.loc_trk = 0.0;
+  S.c_ev = S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
+  S.need_f = true; S.need_xs = true;
+  S.gmask = 0;
 }
 
-// One warp-uniform step of work distribution: hand photon indices to lanes that want one.
-// Returns the index for this lane or ~0ull.
+__device__ __forceinline__ void pstate_store_full(const PState &S, const PhotonSoA &ph, uint64_t idx) {
+  ph.xy[idx] = make_double2(S.x, S.y);
+  ph.za[idx] = make_double2(S.z, S.ax);
+  ph.bc[idx] = make_double2(S.ay, S.az);
+  ph.lc[idx] = make_ulonglong2((unsigned long long)__double_as_longlong(S.life), S.ctr);
+  ph.sg[idx] = make_ulonglong2(S.stream, (unsigned long long)S.cell | ((unsigned long long)S.group << 32));
+}
+
+__device__ __forceinline__ void close_visit(PState &S) {
+  // distinct (cell, group) opacity pairs touched in this visit (S_cell; group ids are hashed into
+  // 64 bits, so for G > 64 this is a lower bound)
+  S.c_lk += (uint32_t)__popcll(S.gmask);
+  S.gmask = 0;
+}
+
+// One trip of the reference's while(active) loop (src/history_based_transport.h:55-139) up to the event dispatch.
+// Returns R_SCATTER with the scatter not yet sampled (the caller runs scatter_event), R_DONE with `descriptor` set, or
+// R_CONTINUE after a cell crossing / reflection.  `bc` are the six domain boundary conditions.
+template <class Deposit>
+__device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int *bc, Deposit &&deposit,
+                                             uint8_t &descriptor) {
+  if (S.need_f) { S.f = __ldg(&C.f[S.cell]); S.need_f = false; }
+  if (S.need_xs) {
+    const uint64_t o = (uint64_t)S.cell * C.G + S.group;
+    S.sig_a = __ldg(&C.opa[o]);
+    S.sig_s = __ldg(&C.ops[o]);
+    S.need_xs = false;
+    S.gmask |= 1ull << (S.group & 63u);
+  }
+  const double total_sigma_s = (1.0 - S.f) * S.sig_a + S.sig_s;
+  double d_scat = 1.0e100;
+  if (total_sigma_s > 0.0) d_scat = -log(rng_next(S.ctr, C.ctr_hi, S.stream)) / total_sigma_s;
+
+  // distance to boundary: strict-minimum scan over x, y, z starting from 1e16 (src/cell.h:116-132)
+  double d_bnd = 1.0e16;
+  {
+    const bool px = 0.0 < S.ax, py = 0.0 < S.ay, pz = 0.0 < S.az;
+    const double dx = (C.fx[S.i + (px ? 1 : 0)] - S.x) / S.ax;
+    const double dy = (C.fy[S.j + (py ? 1 : 0)] - S.y) / S.ay;
+    const double dz = (C.fz[S.k + (pz ? 1 : 0)] - S.z) / S.az;
+    if (dx < d_bnd) { d_bnd = dx; S.surface = px ? 1u : 0u; }
+    if (dy < d_bnd) { d_bnd = dy; S.surface = 2u + (py ? 1u : 0u); }
+    if (dz < d_bnd) { d_bnd = dz; S.surface = 4u + (pz ? 1u : 0u); }
+  }
+  const double d_cen = S.life;
+  const double m1 = (d_cen < d_bnd) ? d_cen : d_bnd;  // std::min(boundary, census)
+  const double d = (m1 < d_scat) ? m1 : d_scat;       // std::min(scatter, m1)
+
+  const double absorbed = S.E * (1.0 - exp(-S.sig_a * S.f * d));
+  S.loc_abs += absorbed;
+  S.loc_trk += absorbed / (S.sig_a * S.f);
+  S.E = S.E - absorbed;
+  S.x += S.ax * d;
+  S.y += S.ay * d;
+  S.z += S.az * d;
+  S.life -= d;
+  ++S.c_ev;
+
+  if (S.E / S.E0 < K_CUTOFF) {  // energy cutoff first (:85-91)
+    S.loc_abs += S.E;
+    deposit(S.cell, S.loc_abs, S.loc_trk);
+    descriptor = EV_KILLED;
+    return R_DONE;
+  }
+  if (d == d_scat) return R_SCATTER;
+  if (d == d_bnd) {
+    const uint32_t axis = S.surface >> 1;
+    const bool pos_dir = S.surface & 1u;
+    bool domain_face;
+    if (axis == 0) domain_face = pos_dir ? (S.i == (int)C.nx - 1) : (S.i == 0);
+    else if (axis == 1) domain_face = pos_dir ? (S.j == (int)C.ny - 1) : (S.j == 0);
+    else domain_face = pos_dir ? (S.k == (int)C.nz - 1) : (S.k == 0);
+    const int bcv = domain_face ? bc[S.surface] : BC_ELEMENT;
+    if (bcv == BC_ELEMENT) {  // (:104-114)
+      deposit(S.cell, S.loc_abs, S.loc_trk);
+      close_visit(S);
+      const int step = pos_dir ? 1 : -1;
+      if (axis == 0) { S.i += step; S.cell += (uint32_t)step; }
+      else if (axis == 1) { S.j += step; S.cell += (uint32_t)(step * (int)C.nx); }
+      else { S.k += step; S.cell += (uint32_t)(step * (int)C.sxy); }
+      S.loc_abs = 0.0;
+      S.loc_trk = 0.0;
+      S.need_f = true;
+      S.need_xs = true;
+      ++S.c_cr;
+      return R_CONTINUE;
+    }
+    if (bcv == BC_VACUUM || bcv == BC_SOURCE) {  // (:122-126)
+      deposit(S.cell, S.loc_abs, S.loc_trk);
+      descriptor = EV_EXIT;
+      return R_DONE;
+    }
+    if (bcv == BC_PROCESSOR) {
+      // never produced in replicated mode (every rank owns the whole mesh); kept for fidelity (:115-121)
+      deposit(S.cell, S.loc_abs, S.loc_trk);
+      descriptor = EV_PASS;
+      return R_DONE;
+    }
+    // REFLECT (:127-130)
+    if (axis == 0) S.ax = -S.ax;
+    else if (axis == 1) S.ay = -S.ay;
+    else S.az = -S.az;
+    ++S.c_rf;
+    return R_CONTINUE;
+  }
+  if (d == d_cen) {  // (:133-138)
+    deposit(S.cell, S.loc_abs, S.loc_trk);
+    descriptor = EV_CENSUS;
+    return R_DONE;
+  }
+  return R_CONTINUE;  // only reachable through NaN distances (the reference loops as well)
+}
+
+// The scatter event (:94-101).  Its draws use consecutive counters, so they are evaluated as four interleaved
+// Threefry chains: mu, phi (src/sampling_functions.h:57-70), the effective-scatter test (:98) and -- if it passes -- the
+// group CDF value (src/sampling_functions.h:126-138).  An unused fourth value is discarded, its counter not consumed.
+__device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
+  uint64_t w[4];
+  threefry2x64_20_w0_x4(S.ctr, C.ctr_hi, S.stream, w);
+  S.ctr += 3;
+  const double mu = u01_from_bits(w[0]) * 2.0 - 1.0;
+  const double phi = u01_from_bits(w[1]) * 2.0 * K_PI;
+  const double sin_theta = sqrt(1.0 - mu * mu);
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  S.ax = sin_theta * cp;
+  S.ay = sin_theta * sp;
+  S.az = mu;
+  // physical vs effective scatter (src/history_based_transport.h:98-100)
+  if (u01_from_bits(w[2]) > (S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s))) {
+    // sample_emission_group: sequential walk of the cell's group array, same arithmetic, loads batched by four
+    double cdf = u01_from_bits(w[3]);
+    S.ctr += 1;
+    const uint32_t G = C.G;
+    const double *ag = C.opa + (uint64_t)S.cell * G;
+    double a4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a4[q] = (q < (int)G) ? __ldg(&ag[q]) : 0.0;
+    const double norm = 1.0 / (a4[0] * (double)G);
+    int g = -1;
+    for (uint32_t base = 0;;) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (cdf > 0.0 && base + q < G) {
+          g = (int)(base + q);
+          cdf -= a4[q] * norm;
+        }
+      }
+      base += 4;
+      if (!(cdf > 0.0) || base >= G) break;  // g == G-1 here if the walk ran off the end (round-off guard)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a4[q] = (base + q < G) ? __ldg(&ag[base + q]) : 0.0;
+    }
+    if ((uint32_t)g != S.group) { S.group = (uint32_t)g; S.need_xs = true; }
+  }
+  ++S.c_sc;
+}
+
+// per-CTA statistics of a finished history
+__device__ __forceinline__ void stats_add(unsigned long long *s_stats, const PState &S) {
+  atomicAdd(&s_stats[ST_EVENTS], (unsigned long long)S.c_ev);
+  atomicAdd(&s_stats[ST_SCATTERS], (unsigned long long)S.c_sc);
+  atomicAdd(&s_stats[ST_CROSSINGS], (unsigned long long)S.c_cr);
+  atomicAdd(&s_stats[ST_REFLECTIONS], (unsigned long long)S.c_rf);
+  atomicAdd(&s_stats[ST_DEPOSITS], (unsigned long long)S.c_cr + 1ull);  // one per cell left + the final one
+  atomicAdd(&s_stats[ST_LOOKUPS], (unsigned long long)S.c_lk);
+}
+
 struct WarpQueue {
   uint64_t next, end;
   bool exhausted;
 };
 
-template <int MODE, bool COUNTERS, bool SMEM>
-__global__ void __launch_bounds__(128, 4) k_transport_history(const TransportParams P) {
+#ifndef BG_MIN_BLOCKS
+#define BG_MIN_BLOCKS 4
+#endif
+
+// RESUME: the launch continues histories that the event-based passes (event.cuh) parked at a pending scatter: photon
+// indices come from P.index_list, the thread-local tallies and counters from P.carry_*.
+template <int MODE, bool COUNTERS, bool SMEM, bool RESUME>
+__global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const TransportParams P) {
   extern __shared__ double s_faces[];
+  __shared__ unsigned long long s_stats[6];
+  if (threadIdx.x < 6) s_stats[threadIdx.x] = 0ull;
   const double *faces;
   if (SMEM) {
     for (uint32_t t = threadIdx.x; t < P.mesh.n_faces; t += blockDim.x) s_faces[t] = P.mesh.faces[t];
-    __syncthreads();
     faces = s_faces;
   } else {
     faces = P.mesh.faces;
   }
-  const double *fx = faces;
-  const double *fy = faces + (P.mesh.nx + 1);
-  const double *fz = fy + (P.mesh.ny + 1);
-  const uint32_t nx = P.mesh.nx, ny = P.mesh.ny, nz = P.mesh.nz, G = P.mesh.G;
-  const uint32_t sxy = nx * ny;
+  __syncthreads();
+  PCtx C;
+  C.fx = faces;
+  C.fy = faces + (P.mesh.nx + 1);
+  C.fz = C.fy + (P.mesh.ny + 1);
+  C.nx = P.mesh.nx; C.ny = P.mesh.ny; C.nz = P.mesh.nz; C.G = P.mesh.G;
+  C.sxy = C.nx * C.ny;
+  C.f = P.f; C.opa = P.opa; C.ops = P.ops;
+  C.ctr_hi = P.ctr_hi;
   const unsigned FULL = 0xffffffffu;
   const unsigned lane_id = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane_id) - 1u;
-  const uint64_t ctr_hi = P.ctr_hi;
 
   WarpQueue q{0, 0, false};
   bool active = false;
-  Lane L;
-  L.x = L.y = L.z = L.ax = L.ay = L.az = L.E = L.E0 = L.life = 0.0;
-  L.ctr = L.stream = L.idx = 0;
-  L.cell = L.group = 0;
-  L.i = L.j = L.k = 0;
-  double f = 0.0, sig_a = 0.0, sig_s = 0.0;
-  double loc_abs = 0.0, loc_trk = 0.0;
-  uint32_t surface = 0;  // persists across events like the reference's surface_cross (:37)
-  uint32_t c_ev = 0, c_sc = 0, c_cr = 0, c_rf = 0;  // per-photon counters
-  uint32_t t_ev = 0, t_sc = 0, t_cr = 0, t_rf = 0, t_dep = 0, t_lk = 0;  // per-thread totals
-  uint64_t gmask = 0;  // groups touched during the current cell visit (algorithmic-bytes accounting)
-  uint32_t lk_visit = 0;
+  bool pending_scatter = false;
+  PState S;
+  S.x = S.y = S.z = S.ax = S.ay = S.az = S.E = S.E0 = S.life = 0.0;
+  S.ctr = S.stream = 0;
+  S.cell = S.group = 0;
+  S.i = S.j = S.k = 0;
+  S.f = S.sig_a = S.sig_s = S.loc_abs = S.loc_trk = 0.0;
+  S.surface = 0;
+  S.c_ev = S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
+  S.gmask = 0;
+  S.need_f = S.need_xs = false;
+  uint64_t my_idx = 0;
   uint32_t ndep = 0;
   uint64_t dep_pos = 0;
-  bool need_f = false, need_xs = false;
-
-  auto close_visit = [&]() {
-    // distinct (cell, group) opacity pairs touched in this visit, capped at G (S_cell)
-    t_lk += (G <= 64) ? (uint32_t)__popcll(gmask) : min(lk_visit, G);
-    gmask = 0;
-    lk_visit = 0;
-  };
 
   auto deposit = [&](uint32_t cell, double a, double t) {
-    ++t_dep;
     if (MODE == TM_ATOMIC) {
       atomicAdd(&P.tally[cell].x, a);
       atomicAdd(&P.tally[cell].y, t);
@@ -146,27 +349,20 @@ __global__ void __launch_bounds__(128, 4) k_transport_history(const TransportPar
         const uint64_t avail = q.end - q.next;
         const unsigned r = __popc(m & lt_mask);
         if (want && r < avail) {
-          const uint64_t idx = q.next + r;
-          const double2 xy = P.ph.xy[idx], za = P.ph.za[idx], bc = P.ph.bc[idx], ee = P.ph.ee[idx];
-          const ulonglong2 lc = P.ph.lc[idx], sg = P.ph.sg[idx];
-          L.x = xy.x; L.y = xy.y; L.z = za.x; L.ax = za.y; L.ay = bc.x; L.az = bc.y;
-          L.E = ee.x; L.E0 = ee.y;
-          L.life = __longlong_as_double((long long)lc.x);
-          L.ctr = lc.y;
-          L.stream = sg.x;
-          L.cell = (uint32_t)sg.y;
-          L.group = (uint32_t)(sg.y >> 32);
-          L.idx = idx;
-          const uint32_t kk = L.cell / sxy;
-          const uint32_t rem = L.cell - kk * sxy;
-          const uint32_t jj = rem / nx;
-          L.k = (int)kk; L.j = (int)jj; L.i = (int)(rem - jj * nx);
-          loc_abs = 0.0; loc_trk = 0.0;
-          c_ev = c_sc = c_cr = c_rf = 0;
+          const uint64_t slot = q.next + r;
+          const uint64_t idx = RESUME ? (uint64_t)P.index_list[slot] : slot;
+          pstate_load(S, P.ph, idx, C);
+          my_idx = idx;
+          if (RESUME) {
+            const double2 acc = P.carry_acc[idx];
+            const uint4 cn = P.carry_cnt[idx];
+            S.loc_abs = acc.x; S.loc_trk = acc.y;
+            S.c_ev = cn.x; S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
+            S.c_lk = P.carry_lk[idx];
+            pending_scatter = true;
+          }
           ndep = 0;
           if (MODE == TM_LOG) dep_pos = P.dep_off[idx];
-          need_f = true; need_xs = true;
-          gmask = 0; lk_visit = 0;
           active = true;
           want = false;
         }
@@ -178,151 +374,41 @@ __global__ void __launch_bounds__(128, 4) k_transport_history(const TransportPar
     }
     if (!active) continue;
 
-    // ---------------- one event (one trip of the reference's while(active) loop) ----------------
-    if (need_f) { f = __ldg(&P.f[L.cell]); need_f = false; }
-    if (need_xs) {
-      const uint64_t o = (uint64_t)L.cell * G + L.group;
-      sig_a = __ldg(&P.opa[o]);
-      sig_s = __ldg(&P.ops[o]);
-      need_xs = false;
-      if (G <= 64) gmask |= 1ull << L.group;
-      ++lk_visit;
+    // ---------------- one event ----------------
+    if (RESUME && pending_scatter) {
+      // the parked scatter needs this visit's cell data (sigma_s, f, sigma_a) before it can be sampled
+      S.f = __ldg(&C.f[S.cell]);
+      const uint64_t o = (uint64_t)S.cell * C.G + S.group;
+      S.sig_a = __ldg(&C.opa[o]);
+      S.sig_s = __ldg(&C.ops[o]);
+      S.need_f = false; S.need_xs = false;
+      S.gmask |= 1ull << (S.group & 63u);
+      scatter_event(S, C);
+      pending_scatter = false;
     }
-    const double total_sigma_s = (1.0 - f) * sig_a + sig_s;
-    double d_scat = 1.0e100;
-    if (total_sigma_s > 0.0) d_scat = -log(rng_next(L.ctr, ctr_hi, L.stream)) / total_sigma_s;
-
-    // distance to boundary: strict-minimum scan over x, y, z starting from 1e16 (src/cell.h:116-132)
-    double d_bnd = 1.0e16;
-    {
-      const bool px = 0.0 < L.ax, py = 0.0 < L.ay, pz = 0.0 < L.az;
-      const double dx = (fx[L.i + (px ? 1 : 0)] - L.x) / L.ax;
-      const double dy = (fy[L.j + (py ? 1 : 0)] - L.y) / L.ay;
-      const double dz = (fz[L.k + (pz ? 1 : 0)] - L.z) / L.az;
-      if (dx < d_bnd) { d_bnd = dx; surface = px ? 1u : 0u; }
-      if (dy < d_bnd) { d_bnd = dy; surface = 2u + (py ? 1u : 0u); }
-      if (dz < d_bnd) { d_bnd = dz; surface = 4u + (pz ? 1u : 0u); }
-    }
-    const double d_cen = L.life;
-    const double m1 = (d_cen < d_bnd) ? d_cen : d_bnd;    // std::min(boundary, census)
-    const double d = (m1 < d_scat) ? m1 : d_scat;         // std::min(scatter, m1)
-
-    const double absorbed = L.E * (1.0 - exp(-sig_a * f * d));
-    loc_abs += absorbed;
-    loc_trk += absorbed / (sig_a * f);
-    L.E = L.E - absorbed;
-    L.x += L.ax * d;
-    L.y += L.ay * d;
-    L.z += L.az * d;
-    L.life -= d;
-    ++c_ev;
-
     uint8_t descriptor = EV_PASS;
-    bool done = false;
-    if (L.E / L.E0 < K_CUTOFF) {
-      loc_abs += L.E;
-      deposit(L.cell, loc_abs, loc_trk);
-      descriptor = EV_KILLED;
-      done = true;
-    } else if (d == d_scat) {
-      // isotropic re-emission direction (src/sampling_functions.h:57-70)
-      const double mu = rng_next(L.ctr, ctr_hi, L.stream) * 2.0 - 1.0;
-      const double phi = rng_next(L.ctr, ctr_hi, L.stream) * 2.0 * K_PI;
-      const double sin_theta = sqrt(1.0 - mu * mu);
-      double sp, cp;
-      sincos(phi, &sp, &cp);
-      L.ax = sin_theta * cp;
-      L.ay = sin_theta * sp;
-      L.az = mu;
-      // physical vs effective scatter (src/history_based_transport.h:98-100)
-      if (rng_next(L.ctr, ctr_hi, L.stream) > (sig_s / ((1.0 - f) * sig_a + sig_s))) {
-        // sample_emission_group (src/sampling_functions.h:126-138): sequential walk of the cell's group array
-        double cdf = rng_next(L.ctr, ctr_hi, L.stream);
-        const double *ag = P.opa + (uint64_t)L.cell * G;
-        const double norm = 1.0 / (__ldg(&ag[0]) * (double)G);
-        int g = -1;
-        while (cdf > 0.0) {
-          ++g;
-          if (g >= (int)G) { g = (int)G - 1; break; }  // round-off guard: the reference would read past the array
-          cdf -= __ldg(&ag[g]) * norm;
-        }
-        if ((uint32_t)g != L.group) { L.group = (uint32_t)g; need_xs = true; }
-      }
-      ++c_sc;
-    } else if (d == d_bnd) {
-      const uint32_t axis = surface >> 1;
-      const bool pos_dir = surface & 1u;
-      bool domain_face;
-      if (axis == 0) domain_face = pos_dir ? (L.i == (int)nx - 1) : (L.i == 0);
-      else if (axis == 1) domain_face = pos_dir ? (L.j == (int)ny - 1) : (L.j == 0);
-      else domain_face = pos_dir ? (L.k == (int)nz - 1) : (L.k == 0);
-      const int bcv = domain_face ? P.mesh.bc[surface] : BC_ELEMENT;
-      if (bcv == BC_ELEMENT) {
-        deposit(L.cell, loc_abs, loc_trk);
-        close_visit();
-        const int step = pos_dir ? 1 : -1;
-        if (axis == 0) { L.i += step; L.cell += (uint32_t)step; }
-        else if (axis == 1) { L.j += step; L.cell += (uint32_t)(step * (int)nx); }
-        else { L.k += step; L.cell += (uint32_t)(step * (int)sxy); }
-        loc_abs = 0.0;
-        loc_trk = 0.0;
-        need_f = true;
-        need_xs = true;
-        ++c_cr;
-      } else if (bcv == BC_VACUUM || bcv == BC_SOURCE) {
-        deposit(L.cell, loc_abs, loc_trk);
-        descriptor = EV_EXIT;
-        done = true;
-      } else if (bcv == BC_PROCESSOR) {
-        // never produced in replicated mode (every rank owns the whole mesh); kept for fidelity (:115-121)
-        deposit(L.cell, loc_abs, loc_trk);
-        descriptor = EV_PASS;
-        done = true;
-      } else {  // REFLECT (:127-130)
-        if (axis == 0) L.ax = -L.ax;
-        else if (axis == 1) L.ay = -L.ay;
-        else L.az = -L.az;
-        ++c_rf;
-      }
-    } else if (d == d_cen) {
-      deposit(L.cell, loc_abs, loc_trk);
-      descriptor = EV_CENSUS;
-      done = true;
-    }
-
-    if (done) {
-      close_visit();
-      t_ev += c_ev; t_sc += c_sc; t_cr += c_cr; t_rf += c_rf;
-      const uint64_t idx = L.idx;
+    const int r = advance_event(S, C, P.mesh.bc, deposit, descriptor);
+    if (r == R_SCATTER) {
+      scatter_event(S, C);
+    } else if (r == R_DONE) {
+      close_visit(S);
+      if (MODE != TM_COUNT) stats_add(s_stats, S);
+      const uint64_t idx = my_idx;
       if (MODE == TM_COUNT) {
         P.ndep[idx] = ndep;
       } else {
         P.desc[idx] = descriptor;
-        P.ph.ee[idx] = make_double2(L.E, L.E0);
-        if (P.writeback_all || descriptor == EV_CENSUS) {
-          P.ph.xy[idx] = make_double2(L.x, L.y);
-          P.ph.za[idx] = make_double2(L.z, L.ax);
-          P.ph.bc[idx] = make_double2(L.ay, L.az);
-          P.ph.lc[idx] = make_ulonglong2((unsigned long long)__double_as_longlong(L.life), L.ctr);
-          P.ph.sg[idx] = make_ulonglong2(L.stream, (unsigned long long)L.cell | ((unsigned long long)L.group << 32));
-        }
-        if (COUNTERS) reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(c_ev, c_sc, c_cr, c_rf);
+        P.ph.ee[idx] = make_double2(S.E, S.E0);
+        if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
+        if (COUNTERS) reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
       }
       active = false;
     }
   }
 
-  // ---------------- statistics: warp reduce, one atomic per warp and counter ----------------
-  if (MODE != TM_COUNT) {
-    unsigned long long v[6] = {t_ev, t_sc, t_cr, t_rf, t_dep, t_lk};
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      unsigned long long x = v[s];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-      if (lane_id == 0 && x) atomicAdd(&P.stats[s], x);
-    }
-  }
+  // ---------------- statistics: one global atomic per CTA and counter ----------------
+  __syncthreads();
+  if (MODE != TM_COUNT && threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 }  // namespace bg

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbranson_gpu.so")
+# BRANSON_GPU_LIB: developer knob to load an experimental build of the same ABI (tools/, never the tests or bench)
+LIB_PATH = os.environ.get("BRANSON_GPU_LIB") or os.path.join(_HERE, "libbranson_gpu.so")
 
 ABI_VERSION = 1
 HISTORY, EVENT = 0, 1
@@ -54,7 +55,7 @@ EXPORTS = [
     "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
-    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_test_rng_draws", "bgpu_test_threefry",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_test_rng_draws", "bgpu_test_threefry",
 ]
 
 
@@ -89,6 +90,7 @@ def lib():
         L.bgpu_list_size.restype = u64
         L.bgpu_enable_counters.argtypes = [vp, i32]
         L.bgpu_set_launch.argtypes = [vp, i32, i32, i32]
+        L.bgpu_set_event_tail.argtypes = [vp, u64]
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
         L.bgpu_test_threefry.argtypes = [vp, vp]
         _LIB = L
@@ -202,6 +204,9 @@ class Context:
 
     def set_launch(self, block_threads=0, blocks_per_sm=0, chunk=0):
         self._ck(lib().bgpu_set_launch(self._h, block_threads, blocks_per_sm, chunk))
+
+    def set_event_tail(self, n_active):
+        self._ck(lib().bgpu_set_event_tail(self._h, n_active))
 
     def list_size(self, which=LIST_WORK):
         return lib().bgpu_list_size(self._h, which)

@@ -157,6 +157,9 @@ int bgpu_enable_counters(bgpu_ctx *ctx, int on);
 
 /* tuning knobs (defaults chosen for B200: 148 SMs) */
 int bgpu_set_launch(bgpu_ctx *ctx, int block_threads, int blocks_per_sm, int chunk_photons);
+/* BGPU_EVENT: active-list size at or below which the lockstep passes hand the remaining histories to the persistent
+ * history kernel (0 = auto: twice the number of resident lanes) */
+int bgpu_set_event_tail(bgpu_ctx *ctx, uint64_t n_active);
 
 /* known-answer hooks for the RNG unit tests (RNG(seed, stream) draws, src/RNG.h:262-285,318-330; raw Threefry2x64-20
  * of {ctr0, ctr1, key0, key1}, src/random123/threefry.h:196-282) */

@@ -32,7 +32,8 @@ def _close(got, want, scale=None, what=""):
     return float(err.max() / s) if s > 0 else 0.0
 
 
-def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATOMIC, max_cycles=None, launch=None):
+def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATOMIC, max_cycles=None, launch=None,
+                event_tail=None):
     sim = port.OracleSim(deck, n_ranks=n_ranks)
     ctxs = None
     cyc = 0
@@ -47,6 +48,8 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
                 c.enable_counters(True)
                 if launch:
                     c.set_launch(**launch)
+                if event_tail is not None:
+                    c.set_event_tail(event_tail)
         dt, next_dt, gse = sim.get("dt")[0], sim.get("next_dt")[0], sim.get("global_source_energy")[0]
         f, op_a, op_s = sim.get("f"), sim.get("op_a"), sim.get("op_s")
         tot_abs = np.zeros(deck.n_cells)
@@ -153,6 +156,15 @@ def test_history_atomic_matches_oracle(name):
 def test_history_deterministic_matches_oracle(name):
     mk, n_ranks = CASES[name]
     _run_cycles(mk(), n_ranks=n_ranks, tally_mode=gpu.TALLY_DETERMINISTIC)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("event_tail", [1, 2000])
+def test_event_variant_matches_oracle(name, event_tail):
+    """The event-based variant must reproduce the HISTORY results photon by photon (SURVEY 8a note N5): lockstep passes
+    all the way down (tail 1) and with the history kernel finishing the last 2000 histories (RESUME path)."""
+    mk, n_ranks = CASES[name]
+    _run_cycles(mk(), n_ranks=n_ranks, algorithm=gpu.EVENT, event_tail=event_tail)
 
 
 def test_deterministic_mode_is_bitwise_reproducible():
