@@ -329,17 +329,18 @@ int launch_history(bgpu_ctx *c, const TransportParams &P) {
   return 0;
 }
 
-// BGPU_EVENT: lockstep passes regrouped at scatters (event.cuh), tail finished by the history kernel in RESUME mode
+// BGPU_EVENT: lockstep passes over two active lists (event.cuh), tail finished by the history kernel in RESUME mode
 int run_event(bgpu_ctx *c, TransportParams P) {
   const uint64_t n = P.n;
-  const size_t bytes = 16 * n + 16 * n + 4 * n + 4 * n + 4 * n + 64;
+  const size_t bytes = 16 * n + 16 * n + 4 * n + 4 * 4 * n + 64;
   if (ensure(c, c->scr_event, bytes)) return 1;
   char *p = (char *)c->scr_event.p;
   double2 *acc = (double2 *)p;                 p += 16 * n;
   uint4 *cnt = (uint4 *)p;                     p += 16 * n;
   uint32_t *lk = (uint32_t *)p;                p += 4 * n;
-  uint32_t *list_a = (uint32_t *)p;            p += 4 * n;
-  uint32_t *list_b = (uint32_t *)p;            p += 4 * n;
+  uint32_t *lists[2][2];                       // [ping-pong][0 scatter, 1 continue]
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) { lists[a][b] = (uint32_t *)p; p += 4 * n; }
   unsigned long long *n_out = (unsigned long long *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   const size_t smem = (size_t)P.mesh.n_faces * 8;
   const bool use_smem = smem <= 160 * 1024;
@@ -358,36 +359,44 @@ int run_event(bgpu_ctx *c, TransportParams P) {
   E.T = P;
   E.acc = acc; E.cnt = cnt; E.lk = lk;
   E.n_out = n_out;
-  uint64_t n_active = n;
-  const uint32_t *list_in = nullptr;
-  uint32_t *list_out = list_a;
+  uint64_t n_in[2] = {0, n};  // first pass: everything is on the "continue" list (identity order)
+  int cur = 0;
   bool first = true;
   c->event_passes = 0;
-  while (n_active > 0) {
-    if (!first && n_active <= tail) {
-      TransportParams R = P;
-      R.n = n_active;
-      R.index_list = list_in;
-      R.carry_acc = acc; R.carry_cnt = cnt; R.carry_lk = lk;
-      CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
-      if (launch_history<TM_ATOMIC, true>(c, R)) return 1;
+  while (n_in[0] + n_in[1] > 0) {
+    if (!first && n_in[0] + n_in[1] <= tail) {
+      for (int kind = 0; kind < 2; ++kind) {
+        if (!n_in[kind]) continue;
+        TransportParams R = P;
+        R.n = n_in[kind];
+        R.index_list = lists[cur][kind];
+        R.carry_acc = acc; R.carry_cnt = cnt; R.carry_lk = lk;
+        R.resume_pending_scatter = kind == 0 ? 1 : 0;
+        CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
+        if (launch_history<TM_ATOMIC, true>(c, R)) return 1;
+      }
       break;
     }
-    CU(c, cudaMemsetAsync(n_out, 0, 8, c->stream));
-    E.list_in = list_in;
-    E.n_in = n_active;
-    E.list_out = list_out;
-    E.first = first ? 1 : 0;
-    uint64_t blocks = std::min<uint64_t>((n_active + 127) / 128, (uint64_t)c->n_sm * per_sm * 4);
-    ++c->launches;
-    kern<<<(unsigned)blocks, 128, use_smem ? smem : 0, c->stream>>>(E);
-    CU(c, cudaGetLastError());
-    unsigned long long h = 0;
-    CU(c, cudaMemcpyAsync(&h, n_out, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemsetAsync(n_out, 0, 16, c->stream));
+    for (int kind = 0; kind < 2; ++kind) {
+      if (!n_in[kind]) continue;
+      E.list_in = first ? nullptr : lists[cur][kind];
+      E.n_in = n_in[kind];
+      E.scatter_out = lists[cur ^ 1][0];
+      E.cont_out = lists[cur ^ 1][1];
+      E.first = first ? 1 : 0;
+      E.pending_scatter = (!first && kind == 0) ? 1 : 0;
+      const uint64_t blocks = std::min<uint64_t>((n_in[kind] + 127) / 128, (uint64_t)c->n_sm * per_sm * 4);
+      ++c->launches;
+      kern<<<(unsigned)blocks, 128, use_smem ? smem : 0, c->stream>>>(E);
+      CU(c, cudaGetLastError());
+    }
+    unsigned long long h[2] = {0, 0};
+    CU(c, cudaMemcpyAsync(h, n_out, 16, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    n_active = h;
-    list_in = list_out;
-    list_out = (list_out == list_a) ? list_b : list_a;
+    n_in[0] = h[0];
+    n_in[1] = h[1];
+    cur ^= 1;
     first = false;
     ++c->event_passes;
   }

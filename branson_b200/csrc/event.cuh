@@ -5,14 +5,17 @@
 // the (effective) scatter -- 4 of the ~5 Threefry draws of an event, sincos, sqrt and the sequential group walk -- so
 // the photons are regrouped at scatters:
 //
-//   pass k:   for every photon of the active list, in lockstep:   [sample the scatter parked by pass k-1]
-//             then advance (distance sampling, implicit capture, cell crossings, reflections) until the history ends or
-//             the next scatter is reached; survivors park there and are appended to the next active list.
+//   pass k:   two active lists come out of pass k-1: photons parked AT a scatter, and photons parked after a cell
+//             crossing / reflection.  The scatter list is processed by a launch in which every lane samples its scatter
+//             (100% lane efficiency in that phase) and then advances; the other list by a launch that only advances.
+//             "Advance" = at most EV_MAX_ADVANCE trips of the reference's loop (distance sampling, implicit capture,
+//             boundary handling), so no lane waits for a neighbour that streams through many cells.  Finished
+//             histories are written back; the rest is appended (warp-aggregated) to the two lists of pass k+1.
 //
-// Every lane of a warp therefore executes the scatter code together (100% lane efficiency in that phase), the kernel
-// carries no refill logic, and photon state streams through HBM once per scatter (coalesced 128-bit streams + 40 bytes
-// of carried thread-local tallies and counters).  When the active list no longer fills the machine the remaining
-// histories are finished by the persistent history kernel in RESUME mode.
+// The kernels carry no refill logic and no divergent scatter branch; the price is that photon state streams through
+// HBM once per pass (six 128-bit streams + 36 bytes of carried thread-local tallies and counters).  When the active
+// lists no longer fill the machine the remaining histories are finished by the persistent history kernel in RESUME
+// mode.  Measured on the 30-group hohlraum the HISTORY kernel stays the faster of the two.
 //
 // Per-photon results are identical to the HISTORY variant by construction (the same advance_event / scatter_event
 // device functions run in the same per-photon order; only the tally summation order differs) -- unlike the reference,
@@ -24,16 +27,22 @@
 
 namespace bg {
 
+#ifndef EV_MAX_ADVANCE
+#define EV_MAX_ADVANCE 2
+#endif
+
 struct EventParams {
   TransportParams T;
   const uint32_t *list_in;   // nullptr on the first pass: identity
   uint64_t n_in;
-  uint32_t *list_out;
-  unsigned long long *n_out;
+  uint32_t *scatter_out;     // photons parked at a scatter
+  uint32_t *cont_out;        // photons parked after EV_MAX_ADVANCE non-scatter events
+  unsigned long long *n_out; // [0] scatter list size, [1] continue list size
   double2 *acc;              // carried {loc_abs, loc_trk}
   uint4 *cnt;                // carried counters
   uint32_t *lk;
-  int first;
+  int first;                 // no carried state yet
+  int pending_scatter;       // list_in holds photons parked at a scatter
 };
 
 template <bool COUNTERS, bool SMEM>
@@ -69,7 +78,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
   const uint64_t n_round = (E.n_in + 31) & ~31ull;  // whole warps stay converged for the ballots below
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
     const bool valid = t < E.n_in;
-    bool survivor = false;
+    int park = 0;  // 1: at a scatter, 2: after a non-scatter event
     uint64_t idx = 0;
     if (valid) {
       idx = E.list_in ? (uint64_t)E.list_in[t] : t;
@@ -82,6 +91,8 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         S.loc_abs = acc.x; S.loc_trk = acc.y;
         S.c_ev = cn.x; S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
         S.c_lk = E.lk[idx];
+      }
+      if (E.pending_scatter) {
         // the parked scatter: every lane of the warp is here together
         S.f = __ldg(&C.f[S.cell]);
         const uint64_t o = (uint64_t)S.cell * C.G + S.group;
@@ -92,10 +103,10 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         scatter_event(S, C);
       }
       uint8_t descriptor = EV_PASS;
-      int r;
-      do {
+      int r = R_CONTINUE;
+#pragma unroll 1
+      for (int step = 0; step < EV_MAX_ADVANCE && r == R_CONTINUE; ++step)
         r = advance_event(S, C, P.mesh.bc, deposit, descriptor);
-      } while (r == R_CONTINUE);
       if (r == R_DONE) {
         close_visit(S);
         stats_add(s_stats, S);
@@ -103,23 +114,28 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         P.ph.ee[idx] = make_double2(S.E, S.E0);
         if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
         if (COUNTERS) reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
-      } else {  // parked at a scatter
+      } else {  // parked
         close_visit(S);  // the lookup count restarts with the reload of the next pass
         P.ph.ee[idx] = make_double2(S.E, S.E0);
         pstate_store_full(S, P.ph, idx);
         E.acc[idx] = make_double2(S.loc_abs, S.loc_trk);
         E.cnt[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
         E.lk[idx] = S.c_lk;
-        survivor = true;
+        park = (r == R_SCATTER) ? 1 : 2;
       }
     }
-    // warp-aggregated append of the survivors to the next active list
-    const unsigned m = __ballot_sync(0xffffffffu, survivor);
-    if (m) {
-      unsigned long long base = 0;
-      if (lane_id == (unsigned)(__ffs(m) - 1)) base = atomicAdd(E.n_out, (unsigned long long)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-      if (survivor) E.list_out[base + __popc(m & ((1u << lane_id) - 1u))] = (uint32_t)idx;
+    // warp-aggregated append of the survivors to the two active lists of the next pass
+#pragma unroll
+    for (int kind = 1; kind <= 2; ++kind) {
+      const unsigned m = __ballot_sync(0xffffffffu, park == kind);
+      if (m) {
+        unsigned long long base = 0;
+        const int leader = __ffs(m) - 1;
+        if ((int)lane_id == leader) base = atomicAdd(&E.n_out[kind - 1], (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (park == kind)
+          (kind == 1 ? E.scatter_out : E.cont_out)[base + __popc(m & ((1u << lane_id) - 1u))] = (uint32_t)idx;
+      }
     }
   }
   __syncthreads();

@@ -48,6 +48,7 @@ struct TransportParams {
   const double2 *carry_acc;
   const uint4 *carry_cnt;
   const uint32_t *carry_lk;
+  int resume_pending_scatter;  // the photons of index_list are parked AT a scatter (else after a non-scatter event)
 };
 
 // Photon state of one lane, kept in registers for the whole history.
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
             S.loc_abs = acc.x; S.loc_trk = acc.y;
             S.c_ev = cn.x; S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
             S.c_lk = P.carry_lk[idx];
-            pending_scatter = true;
+            pending_scatter = P.resume_pending_scatter != 0;
           }
           ndep = 0;
           if (MODE == TM_LOG) dep_pos = P.dep_off[idx];
