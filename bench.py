@@ -219,6 +219,10 @@ def ncu_traffic():
 
 
 def our_arm(args):
+    # host physics (calculate_photon_energy / update_temperature) is OpenMP: give each rank its share of the cores
+    # (torchrun would otherwise pin every process to OMP_NUM_THREADS=1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_cores() // max(1, local_world)))
     import torch
 
     from branson_b200 import driver, gpu

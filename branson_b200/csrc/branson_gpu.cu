@@ -51,6 +51,8 @@ struct bgpu_ctx {
   double *d_f = nullptr, *d_opa = nullptr, *d_ops = nullptr;  // f [n_cells]; opa/ops [n_cells*G]
   double *d_cell_stage = nullptr;                               // 3*n_cells staging (gray values / E arrays)
   bool have_cell_data = false;
+  bool closed_form_walk = true;
+  bool uniform_groups = false;  // all groups of every cell equal (always true for bgpu_set_cell_data)
 
   // photons
   PhotonSoA work{}, census{};
@@ -191,6 +193,16 @@ __global__ void k_expand_groups(uint32_t n_cells, uint32_t G, const double *__re
   const uint32_t cell = (uint32_t)(t / G);
   opa[t] = a[cell];
   ops[t] = s[cell];
+}
+
+__global__ void k_count_nonuniform_cells(uint32_t n_cells, uint32_t G, const double *__restrict__ opa,
+                                         unsigned long long *count) {
+  const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const double *a = opa + (uint64_t)cell * G;
+  bool same = true;
+  for (uint32_t g = 1; g < G; ++g) same = same && (a[g] == a[0]);
+  if (!same) atomicAdd(count, 1ull);
 }
 
 __global__ void k_copy_soa(PhotonSoA src, uint64_t src_off, PhotonSoA dst, uint64_t dst_off, uint64_t n) {
@@ -419,6 +431,7 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   P.chunk = c->chunk;
   P.writeback_all = writeback_all ? 1 : 0;
   P.stats = c->d_stats;
+  P.uniform_groups = (c->uniform_groups && c->closed_form_walk) ? 1 : 0;
   return P;
 }
 
@@ -694,6 +707,7 @@ int bgpu_set_cell_data(bgpu_ctx *c, const double *f, const double *op_a, const d
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));  // the host arrays may be rewritten as soon as we return
   c->have_cell_data = true;
+  c->uniform_groups = true;
   return 0;
 }
 
@@ -704,8 +718,14 @@ int bgpu_set_cell_groups(bgpu_ctx *c, const double *f, const double *abs_groups,
   CU(c, cudaMemcpyAsync(c->d_f, f, 8 * nc, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(c->d_opa, abs_groups, 8 * nc * G, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemcpyAsync(c->d_ops, sct_groups, 8 * nc * G, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
+  ++c->launches;
+  k_count_nonuniform_cells<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_opa, c->d_stats);
+  unsigned long long nonuniform = 0;
+  CU(c, cudaMemcpyAsync(&nonuniform, c->d_stats, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   c->have_cell_data = true;
+  c->uniform_groups = nonuniform == 0;
   return 0;
 }
 
@@ -917,6 +937,12 @@ int bgpu_set_launch(bgpu_ctx *c, int block_threads, int blocks_per_sm, int chunk
   }
   c->blocks_per_sm = blocks_per_sm;
   if (chunk > 0) c->chunk = (uint32_t)chunk;
+  return 0;
+}
+
+int bgpu_set_group_walk(bgpu_ctx *c, int closed_form) {
+  if (!c) return 1;
+  c->closed_form_walk = closed_form != 0;
   return 0;
 }
 

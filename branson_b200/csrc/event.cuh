@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
   C.sxy = C.nx * C.ny;
   C.f = P.f; C.opa = P.opa; C.ops = P.ops;
   C.ctr_hi = P.ctr_hi;
+  C.uniform_groups = P.uniform_groups != 0;
   const unsigned lane_id = threadIdx.x & 31u;
 
   auto deposit = [&](uint32_t cell, double a, double t) {
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
       idx = E.list_in ? (uint64_t)E.list_in[t] : t;
       PState S;
       S.surface = 0;
+      S.p_grp = 0.0;
       pstate_load(S, P.ph, idx, C);
       if (!E.first) {
         const double2 acc = E.acc[idx];

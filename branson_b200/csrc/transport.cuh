@@ -48,6 +48,7 @@ struct TransportParams {
   const double2 *carry_acc;
   const uint4 *carry_cnt;
   const uint32_t *carry_lk;
+  int uniform_groups;  // every cell's abs_groups are all equal (gray decks, Cell::set_op_a): closed-form group walk
   int resume_pending_scatter;  // the photons of index_list are parked AT a scatter (else after a non-scatter event)
 };
 
@@ -59,10 +60,11 @@ struct PState {
   int i, j, k;
   double f, sig_a, sig_s;        // cell / group data of the current visit
   double loc_abs, loc_trk;       // thread-local tallies of the current cell visit (reference :45-46)
+  double p_grp;                  // abs_groups[g] * norm of the current cell when all its groups are equal (lazy)
   uint32_t surface;              // persists across events like the reference's surface_cross (:37)
   uint32_t c_ev, c_sc, c_cr, c_rf, c_lk;  // per-photon counters: events, scatters, crossings, reflections, lookups
   uint64_t gmask;                // groups touched during the current cell visit (algorithmic-bytes accounting)
-  bool need_f, need_xs;
+  bool need_f, need_xs, need_p;
 };
 
 struct PCtx {
@@ -70,6 +72,7 @@ struct PCtx {
   uint32_t nx, ny, nz, G, sxy;
   const double *f, *opa, *ops;
   uint64_t ctr_hi;
+  bool uniform_groups;
 };
 
 enum : int { R_CONTINUE = 0, R_DONE = 1, R_SCATTER = 2 };
@@ -90,7 +93,7 @@ __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint
   S.k = (int)kk; S.j = (int)jj; S.i = (int)(rem - jj * C.nx);
   S.loc_abs = 0.0; S.loc_trk = 0.0;
   S.c_ev = S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
-  S.need_f = true; S.need_xs = true;
+  S.need_f = true; S.need_xs = true; S.need_p = true;
   S.gmask = 0;
 }
 
@@ -178,6 +181,7 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int
       S.loc_trk = 0.0;
       S.need_f = true;
       S.need_xs = true;
+      S.need_p = true;
       ++S.c_cr;
       return R_CONTINUE;
     }
@@ -223,11 +227,32 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
   S.ay = sin_theta * sp;
   S.az = mu;
   // physical vs effective scatter (src/history_based_transport.h:98-100)
-  if (u01_from_bits(w[2]) > (S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s))) {
-    // sample_emission_group: sequential walk of the cell's group array, same arithmetic, loads batched by four
+  // sigma_s == 0 (every reference deck): 0 / x is exactly +0, no division needed
+  const double p_phys = (S.sig_s == 0.0) ? 0.0 : S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s);
+  if (u01_from_bits(w[2]) > p_phys) {
     double cdf = u01_from_bits(w[3]);
     S.ctr += 1;
     const uint32_t G = C.G;
+    if (C.uniform_groups && G <= 512) {
+      // All groups of the cell hold the same opacity, so every step of the reference's walk subtracts the same
+      // p = abs_groups[g] * norm and the walk stops at g = min{k : c_(k+1) <= 0}, c_(k+1) = fl(c_k - p).  The rounding
+      // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
+      // clear zero by a margin far above that bound, the sequential result is provably k0 -- no loads, no dependent
+      // chain, no divergence over the walk length.  Otherwise (probability ~1e-11 per scatter) fall through to the walk.
+      if (S.need_p) {
+        S.p_grp = S.sig_a * (1.0 / (S.sig_a * (double)G));
+        S.need_p = false;
+      }
+      const int k0 = (int)(cdf * (double)G);
+      const double before = fma(-(double)k0, S.p_grp, cdf);  // c_k0 up to rounding
+      const double after = before - S.p_grp;                  // c_(k0+1)
+      if (before > 1.0e-13 && after < -1.0e-13 && k0 < (int)G) {
+        if ((uint32_t)k0 != S.group) { S.group = (uint32_t)k0; S.need_xs = true; }
+        ++S.c_sc;
+        return;
+      }
+    }
+    // sample_emission_group: sequential walk of the cell's group array, same arithmetic, loads batched by four
     const double *ag = C.opa + (uint64_t)S.cell * G;
     double a4[4];
 #pragma unroll
@@ -294,6 +319,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   C.sxy = C.nx * C.ny;
   C.f = P.f; C.opa = P.opa; C.ops = P.ops;
   C.ctr_hi = P.ctr_hi;
+  C.uniform_groups = P.uniform_groups != 0;
   const unsigned FULL = 0xffffffffu;
   const unsigned lane_id = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane_id) - 1u;
@@ -310,7 +336,8 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   S.surface = 0;
   S.c_ev = S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
-  S.need_f = S.need_xs = false;
+  S.need_f = S.need_xs = S.need_p = false;
+  S.p_grp = 0.0;
   uint64_t my_idx = 0;
   uint32_t ndep = 0;
   uint64_t dep_pos = 0;

@@ -55,7 +55,7 @@ EXPORTS = [
     "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
-    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_test_rng_draws", "bgpu_test_threefry",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
         L.bgpu_enable_counters.argtypes = [vp, i32]
         L.bgpu_set_launch.argtypes = [vp, i32, i32, i32]
         L.bgpu_set_event_tail.argtypes = [vp, u64]
+        L.bgpu_set_group_walk.argtypes = [vp, i32]
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
         L.bgpu_test_threefry.argtypes = [vp, vp]
         _LIB = L
@@ -207,6 +208,9 @@ class Context:
 
     def set_event_tail(self, n_active):
         self._ck(lib().bgpu_set_event_tail(self._h, n_active))
+
+    def set_group_walk(self, closed_form=True):
+        self._ck(lib().bgpu_set_group_walk(self._h, 1 if closed_form else 0))
 
     def list_size(self, which=LIST_WORK):
         return lib().bgpu_list_size(self._h, which)

@@ -160,6 +160,9 @@ int bgpu_set_launch(bgpu_ctx *ctx, int block_threads, int blocks_per_sm, int chu
 /* BGPU_EVENT: active-list size at or below which the lockstep passes hand the remaining histories to the persistent
  * history kernel (0 = auto: twice the number of resident lanes) */
 int bgpu_set_event_tail(bgpu_ctx *ctx, uint64_t n_active);
+/* sample_emission_group (src/sampling_functions.h:126-138): 1 (default) = when every cell's groups are equal, use the
+ * provably-equivalent closed form of the sequential walk; 0 = always walk the group array like the reference */
+int bgpu_set_group_walk(bgpu_ctx *ctx, int closed_form);
 
 /* known-answer hooks for the RNG unit tests (RNG(seed, stream) draws, src/RNG.h:262-285,318-330; raw Threefry2x64-20
  * of {ctr0, ctr1, key0, key1}, src/random123/threefry.h:196-282) */

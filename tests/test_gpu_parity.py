@@ -33,7 +33,7 @@ def _close(got, want, scale=None, what=""):
 
 
 def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATOMIC, max_cycles=None, launch=None,
-                event_tail=None):
+                event_tail=None, closed_form_walk=True, group_arrays=False):
     sim = port.OracleSim(deck, n_ranks=n_ranks)
     ctxs = None
     cyc = 0
@@ -50,13 +50,18 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
                     c.set_launch(**launch)
                 if event_tail is not None:
                     c.set_event_tail(event_tail)
+                c.set_group_walk(closed_form_walk)
         dt, next_dt, gse = sim.get("dt")[0], sim.get("next_dt")[0], sim.get("global_source_energy")[0]
         f, op_a, op_s = sim.get("f"), sim.get("op_a"), sim.get("op_s")
         tot_abs = np.zeros(deck.n_cells)
         tot_trk = np.zeros(deck.n_cells)
         life_scale = 299.792458 * dt
         for r, ctx in enumerate(ctxs):
-            ctx.set_cell_data(f, op_a, op_s)
+            if group_arrays:  # the general multigroup entry point, fed with the reference's faux-multigroup arrays
+                G = deck.n_groups
+                ctx.set_cell_groups(f, np.repeat(op_a, G), np.repeat(op_s, G))
+            else:
+                ctx.set_cell_data(f, op_a, op_s)
             n_new, n_tot = ctx.source(cyc, dt, sim.get("E_emission", r), sim.get("E_source", r),
                                       sim.get("E_census", r) if cyc == 1 else None, gse)
             assert n_new == int(sim.get("n_new", r)[0])
@@ -165,6 +170,16 @@ def test_event_variant_matches_oracle(name, event_tail):
     all the way down (tail 1) and with the history kernel finishing the last 2000 histories (RESUME path)."""
     mk, n_ranks = CASES[name]
     _run_cycles(mk(), n_ranks=n_ranks, algorithm=gpu.EVENT, event_tail=event_tail)
+
+
+@pytest.mark.parametrize("name", ["three_region_g30_r2", "hohlraum_s5_g30"])
+@pytest.mark.parametrize("group_arrays", [False, True])
+def test_sequential_group_walk_matches_oracle(name, group_arrays):
+    """sample_emission_group walked through the group array exactly like the reference (the default closed form is a
+    provably equivalent shortcut for cells whose groups are all equal; both must give the oracle's integers)."""
+    mk, n_ranks = CASES[name]
+    _run_cycles(mk(), n_ranks=n_ranks, closed_form_walk=False, group_arrays=group_arrays)
+    _run_cycles(mk(), n_ranks=n_ranks, closed_form_walk=True, group_arrays=group_arrays, max_cycles=2)
 
 
 def test_deterministic_mode_is_bitwise_reproducible():
