@@ -443,6 +443,8 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
     return fail(c, "unknown tally mode %d", tally_mode);
   CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
   if (c->n_work == 0) return 0;
+  if (c->n_work >= (1ull << 32)) return fail(c, "bgpu_transport: %llu photons in one work list (limit 2^32 - 1)",
+                                             (unsigned long long)c->n_work);
   TransportParams P = make_params(c, writeback_all);
   if (algorithm == BGPU_EVENT) {
     if (tally_mode != BGPU_TALLY_ATOMIC) return fail(c, "the event-based variant supports BGPU_TALLY_ATOMIC only");
@@ -1062,6 +1064,26 @@ __global__ void k_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *
 __global__ void k_threefry_kat(const uint64_t *in, uint64_t *out) {
   if (threadIdx.x || blockIdx.x) return;
   threefry2x64_20(in, in + 2, out);
+}
+// accuracy hook for fastmath.cuh: which = 0 exp, 1 log, 2 sincos (out = sin, out2 = cos), 3 libdevice sincos
+__global__ void k_fastmath(int which, uint64_t n, const double *in, double *out, double *out2) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double x = in[i];
+    if (which == 0) out[i] = fm_exp_flush(x);
+    else if (which == 1) out[i] = fm_log_pos(x);
+    else if (which == 2) fm_sincos(x, &out[i], &out2[i]);
+    else sincos(x, &out[i], &out2[i]);
+  }
+}
+int bgpu_test_fastmath(int which, uint64_t n, const double *in, double *out, double *out2) {
+  double *d = nullptr;
+  if (cudaMalloc((void **)&d, 24ull * n) != cudaSuccess) return 1;
+  cudaMemcpy(d, in, 8ull * n, cudaMemcpyHostToDevice);
+  k_fastmath<<<296, 256>>>(which, n, d, d + n, d + 2 * n);
+  cudaError_t e = cudaMemcpy(out, d + n, 8ull * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && out2) e = cudaMemcpy(out2, d + 2 * n, 8ull * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e != cudaSuccess;
 }
 int bgpu_test_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *out) {
   double *d = nullptr;

@@ -48,9 +48,9 @@ struct EventParams {
 template <bool COUNTERS, bool SMEM>
 __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
   extern __shared__ double s_faces[];
-  __shared__ unsigned long long s_stats[6];
+  __shared__ uint32_t s_stats[12];
   const TransportParams &P = E.T;
-  if (threadIdx.x < 6) s_stats[threadIdx.x] = 0ull;
+  if (threadIdx.x < 12) s_stats[threadIdx.x] = 0u;
   const double *faces;
   if (SMEM) {
     for (uint32_t t = threadIdx.x; t < P.mesh.n_faces; t += blockDim.x) s_faces[t] = P.mesh.faces[t];
@@ -91,19 +91,11 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         const double2 acc = E.acc[idx];
         const uint4 cn = E.cnt[idx];
         S.loc_abs = acc.x; S.loc_trk = acc.y;
-        S.c_ev = cn.x; S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
+        S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
         S.c_lk = E.lk[idx];
       }
-      if (E.pending_scatter) {
-        // the parked scatter: every lane of the warp is here together
-        S.f = __ldg(&C.f[S.cell]);
-        const uint64_t o = (uint64_t)S.cell * C.G + S.group;
-        S.sig_a = __ldg(&C.opa[o]);
-        S.sig_s = __ldg(&C.ops[o]);
-        S.need_f = false; S.need_xs = false;
-        S.gmask |= 1ull << (S.group & 63u);
-        scatter_event(S, C);
-      }
+      // the parked scatter: every lane of the warp is here together (pstate_load has fetched f, sigma_a, sigma_s)
+      if (E.pending_scatter) scatter_event(S, C);
       uint8_t descriptor = EV_PASS;
       int r = R_CONTINUE;
 #pragma unroll 1
@@ -115,13 +107,14 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         P.desc[idx] = descriptor;
         P.ph.ee[idx] = make_double2(S.E, S.E0);
         if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
-        if (COUNTERS) reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
+        if (COUNTERS)
+          reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(events_of_finished(S), S.c_sc, S.c_cr, S.c_rf);
       } else {  // parked
         close_visit(S);  // the lookup count restarts with the reload of the next pass
         P.ph.ee[idx] = make_double2(S.E, S.E0);
         pstate_store_full(S, P.ph, idx);
         E.acc[idx] = make_double2(S.loc_abs, S.loc_trk);
-        E.cnt[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
+        E.cnt[idx] = make_uint4(0u, S.c_sc, S.c_cr, S.c_rf);
         E.lk[idx] = S.c_lk;
         park = (r == R_SCATTER) ? 1 : 2;
       }
@@ -141,7 +134,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
     }
   }
   __syncthreads();
-  if (threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  stats_flush(s_stats, P.stats);
 }
 
 }  // namespace bg

@@ -13,7 +13,16 @@
 
 namespace bg {
 
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+// 64-bit rotate as two 32-bit funnel shifts (SHF.L.W.U32.HI); a rotation by 32 is a register swap.  The plain
+// (x << n) | (x >> (64 - n)) form compiles to three alu-pipe instructions per rotation on sm_100a, and the alu pipe is
+// what bounds Threefry (tools/ubench/threefry_variants.cu: +10 % draws/s with this form).
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) {
+  const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  const uint32_t a = (n & 32) ? hi : lo, b = (n & 32) ? lo : hi;  // after the optional swap: value = b:a
+  const uint32_t s = (uint32_t)n & 31u;
+  if (s == 0) return ((uint64_t)b << 32) | a;
+  return ((uint64_t)__funnelshift_l(a, b, s) << 32) | __funnelshift_l(b, a, s);
+}
 
 #define BG_TF_ROUND(R)   \
   x0 += x1;              \

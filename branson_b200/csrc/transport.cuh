@@ -17,7 +17,19 @@
 //     deterministic validation mode -- a per-photon deposit log that is later summed in the reference's serial order.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 #include "rng.cuh"
+
+// A/B switches for tools/ timing sweeps (make variant NAME=.. EXTRA=-DBG_FM_LOG=0); the shipped build has all on
+#ifndef BG_FM_LOG
+#define BG_FM_LOG 1
+#endif
+#ifndef BG_FM_EXP
+#define BG_FM_EXP 1
+#endif
+#ifndef BG_FM_SINCOS
+#define BG_FM_SINCOS 1
+#endif
 
 namespace bg {
 
@@ -25,7 +37,7 @@ enum : int { TM_ATOMIC = 0, TM_COUNT = 1, TM_LOG = 2 };
 
 struct TransportParams {
   PhotonSoA ph;
-  uint64_t n;
+  uint64_t n;          // < 2^32 (checked by the launcher): photon indices travel as 32-bit values
   uint8_t *desc;
   uint32_t *counters;  // [n][4] or nullptr
   MeshDev mesh;
@@ -58,13 +70,12 @@ struct PState {
   uint64_t ctr, stream;
   uint32_t cell, group;
   int i, j, k;
-  double f, sig_a, sig_s;        // cell / group data of the current visit
+  double f, sig_a, sig_s;        // cell / group data of the current visit (loaded when the cell or the group changes)
   double loc_abs, loc_trk;       // thread-local tallies of the current cell visit (reference :45-46)
-  double p_grp;                  // abs_groups[g] * norm of the current cell when all its groups are equal (lazy)
+  double p_grp;                  // abs_groups[g] * norm of the current cell when all its groups are equal; 0 = not yet
   uint32_t surface;              // persists across events like the reference's surface_cross (:37)
-  uint32_t c_ev, c_sc, c_cr, c_rf, c_lk;  // per-photon counters: events, scatters, crossings, reflections, lookups
-  uint64_t gmask;                // groups touched during the current cell visit (algorithmic-bytes accounting)
-  bool need_f, need_xs, need_p;
+  uint32_t c_sc, c_cr, c_rf, c_lk;  // per-photon counters: scatters, crossings, reflections, lookups
+  uint32_t gmask;                // groups touched during the current cell visit (algorithmic-bytes accounting)
 };
 
 struct PCtx {
@@ -76,6 +87,25 @@ struct PCtx {
 };
 
 enum : int { R_CONTINUE = 0, R_DONE = 1, R_SCATTER = 2 };
+
+// Every trip of the reference's loop ends in exactly one of: scatter, cell crossing, reflection, or the event that
+// retires the photon -- so the trip count of a finished history needs no counter of its own.
+__device__ __forceinline__ uint32_t events_of_finished(const PState &S) { return S.c_sc + S.c_cr + S.c_rf + 1u; }
+
+// (sigma_a, sigma_s) of the current (cell, group): src/history_based_transport.h:56-57
+__device__ __forceinline__ void load_xs(PState &S, const PCtx &C) {
+  const uint64_t o = (uint64_t)S.cell * C.G + S.group;
+  S.sig_a = __ldg(&C.opa[o]);
+  S.sig_s = __ldg(&C.ops[o]);
+  S.gmask |= 1u << (S.group & 31u);
+}
+
+// entering a cell: Fleck factor (:58) and the opacities of the photon's group
+__device__ __forceinline__ void enter_cell(PState &S, const PCtx &C) {
+  S.f = __ldg(&C.f[S.cell]);
+  S.p_grp = 0.0;
+  load_xs(S, C);
+}
 
 __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint64_t idx, const PCtx &C) {
   const double2 xy = ph.xy[idx], za = ph.za[idx], bc = ph.bc[idx], ee = ph.ee[idx];
@@ -92,9 +122,9 @@ __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint
   const uint32_t jj = rem / C.nx;
   S.k = (int)kk; S.j = (int)jj; S.i = (int)(rem - jj * C.nx);
   S.loc_abs = 0.0; S.loc_trk = 0.0;
-  S.c_ev = S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
-  S.need_f = true; S.need_xs = true; S.need_p = true;
+  S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
+  enter_cell(S, C);
 }
 
 __device__ __forceinline__ void pstate_store_full(const PState &S, const PhotonSoA &ph, uint64_t idx) {
@@ -107,8 +137,8 @@ __device__ __forceinline__ void pstate_store_full(const PState &S, const PhotonS
 
 __device__ __forceinline__ void close_visit(PState &S) {
   // distinct (cell, group) opacity pairs touched in this visit (S_cell; group ids are hashed into
-  // 64 bits, so for G > 64 this is a lower bound)
-  S.c_lk += (uint32_t)__popcll(S.gmask);
+  // 32 bits, so for G > 32 this is a lower bound)
+  S.c_lk += (uint32_t)__popc(S.gmask);
   S.gmask = 0;
 }
 
@@ -118,17 +148,18 @@ __device__ __forceinline__ void close_visit(PState &S) {
 template <class Deposit>
 __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int *bc, Deposit &&deposit,
                                              uint8_t &descriptor) {
-  if (S.need_f) { S.f = __ldg(&C.f[S.cell]); S.need_f = false; }
-  if (S.need_xs) {
-    const uint64_t o = (uint64_t)S.cell * C.G + S.group;
-    S.sig_a = __ldg(&C.opa[o]);
-    S.sig_s = __ldg(&C.ops[o]);
-    S.need_xs = false;
-    S.gmask |= 1ull << (S.group & 63u);
-  }
   const double total_sigma_s = (1.0 - S.f) * S.sig_a + S.sig_s;
   double d_scat = 1.0e100;
-  if (total_sigma_s > 0.0) d_scat = -log(rng_next(S.ctr, C.ctr_hi, S.stream)) / total_sigma_s;
+  if (total_sigma_s > 0.0) {
+    const uint64_t w = threefry2x64_20_w0(S.ctr, C.ctr_hi, S.stream);
+    S.ctr += 1;
+#if BG_FM_LOG
+    // -log(u) / sigma with u = ((w >> 11) | 1) 2^-53 (rng.cuh u01_from_bits): the 2^-53 goes into the exponent
+    d_scat = -fm_log_pos_scaled(__ull2double_rn((w >> 11) | 1ULL), -53) / total_sigma_s;
+#else
+    d_scat = -log(u01_from_bits(w)) / total_sigma_s;
+#endif
+  }
 
   // distance to boundary: strict-minimum scan over x, y, z starting from 1e16 (src/cell.h:116-132)
   double d_bnd = 1.0e16;
@@ -145,7 +176,11 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int
   const double m1 = (d_cen < d_bnd) ? d_cen : d_bnd;  // std::min(boundary, census)
   const double d = (m1 < d_scat) ? m1 : d_scat;       // std::min(scatter, m1)
 
+#if BG_FM_EXP
+  const double absorbed = S.E * (1.0 - fm_exp_flush(-S.sig_a * S.f * d));
+#else
   const double absorbed = S.E * (1.0 - exp(-S.sig_a * S.f * d));
+#endif
   S.loc_abs += absorbed;
   S.loc_trk += absorbed / (S.sig_a * S.f);
   S.E = S.E - absorbed;
@@ -153,7 +188,6 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int
   S.y += S.ay * d;
   S.z += S.az * d;
   S.life -= d;
-  ++S.c_ev;
 
   if (S.E / S.E0 < K_CUTOFF) {  // energy cutoff first (:85-91)
     S.loc_abs += S.E;
@@ -179,10 +213,8 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int
       else { S.k += step; S.cell += (uint32_t)(step * (int)C.sxy); }
       S.loc_abs = 0.0;
       S.loc_trk = 0.0;
-      S.need_f = true;
-      S.need_xs = true;
-      S.need_p = true;
       ++S.c_cr;
+      enter_cell(S, C);
       return R_CONTINUE;
     }
     if (bcv == BC_VACUUM || bcv == BC_SOURCE) {  // (:122-126)
@@ -218,47 +250,46 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
   uint64_t w[4];
   threefry2x64_20_w0_x4(S.ctr, C.ctr_hi, S.stream, w);
   S.ctr += 3;
+  ++S.c_sc;
   const double mu = u01_from_bits(w[0]) * 2.0 - 1.0;
   const double phi = u01_from_bits(w[1]) * 2.0 * K_PI;
   const double sin_theta = sqrt(1.0 - mu * mu);
   double sp, cp;
+#if BG_FM_SINCOS
+  fm_sincos(phi, &sp, &cp);
+#else
   sincos(phi, &sp, &cp);
+#endif
   S.ax = sin_theta * cp;
   S.ay = sin_theta * sp;
   S.az = mu;
   // physical vs effective scatter (src/history_based_transport.h:98-100)
   // sigma_s == 0 (every reference deck): 0 / x is exactly +0, no division needed
   const double p_phys = (S.sig_s == 0.0) ? 0.0 : S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s);
-  if (u01_from_bits(w[2]) > p_phys) {
-    double cdf = u01_from_bits(w[3]);
-    S.ctr += 1;
-    const uint32_t G = C.G;
-    if (C.uniform_groups && G <= 512) {
-      // All groups of the cell hold the same opacity, so every step of the reference's walk subtracts the same
-      // p = abs_groups[g] * norm and the walk stops at g = min{k : c_(k+1) <= 0}, c_(k+1) = fl(c_k - p).  The rounding
-      // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
-      // clear zero by a margin far above that bound, the sequential result is provably k0 -- no loads, no dependent
-      // chain, no divergence over the walk length.  Otherwise (probability ~1e-11 per scatter) fall through to the walk.
-      if (S.need_p) {
-        S.p_grp = S.sig_a * (1.0 / (S.sig_a * (double)G));
-        S.need_p = false;
-      }
-      const int k0 = (int)(cdf * (double)G);
-      const double before = fma(-(double)k0, S.p_grp, cdf);  // c_k0 up to rounding
-      const double after = before - S.p_grp;                  // c_(k0+1)
-      if (before > 1.0e-13 && after < -1.0e-13 && k0 < (int)G) {
-        if ((uint32_t)k0 != S.group) { S.group = (uint32_t)k0; S.need_xs = true; }
-        ++S.c_sc;
-        return;
-      }
-    }
+  if (!(u01_from_bits(w[2]) > p_phys)) return;
+  double cdf = u01_from_bits(w[3]);
+  S.ctr += 1;
+  const uint32_t G = C.G;
+  int g = -1;
+  if (C.uniform_groups && G <= 512) {
+    // All groups of the cell hold the same opacity, so every step of the reference's walk subtracts the same
+    // p = abs_groups[g] * norm and the walk stops at g = min{k : c_(k+1) <= 0}, c_(k+1) = fl(c_k - p).  The rounding
+    // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
+    // clear zero by a margin far above that bound, the sequential result is provably k0 -- no loads, no dependent
+    // chain, no divergence over the walk length.  Otherwise (probability ~1e-11 per scatter) fall through to the walk.
+    if (S.p_grp == 0.0) S.p_grp = S.sig_a * (1.0 / (S.sig_a * (double)G));
+    const int k0 = (int)(cdf * (double)G);
+    const double before = fma(-(double)k0, S.p_grp, cdf);  // c_k0 up to rounding
+    const double after = before - S.p_grp;                  // c_(k0+1)
+    if (before > 1.0e-13 && after < -1.0e-13 && k0 < (int)G) g = k0;
+  }
+  if (g < 0) {
     // sample_emission_group: sequential walk of the cell's group array, same arithmetic, loads batched by four
     const double *ag = C.opa + (uint64_t)S.cell * G;
     double a4[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) a4[q] = (q < (int)G) ? __ldg(&ag[q]) : 0.0;
     const double norm = 1.0 / (a4[0] * (double)G);
-    int g = -1;
     for (uint32_t base = 0;;) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -272,25 +303,33 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) a4[q] = (base + q < G) ? __ldg(&ag[base + q]) : 0.0;
     }
-    if ((uint32_t)g != S.group) { S.group = (uint32_t)g; S.need_xs = true; }
   }
-  ++S.c_sc;
+  if ((uint32_t)g != S.group) {
+    S.group = (uint32_t)g;
+    load_xs(S, C);
+  }
 }
 
-// per-CTA statistics of a finished history
-__device__ __forceinline__ void stats_add(unsigned long long *s_stats, const PState &S) {
-  atomicAdd(&s_stats[ST_EVENTS], (unsigned long long)S.c_ev);
-  atomicAdd(&s_stats[ST_SCATTERS], (unsigned long long)S.c_sc);
-  atomicAdd(&s_stats[ST_CROSSINGS], (unsigned long long)S.c_cr);
-  atomicAdd(&s_stats[ST_REFLECTIONS], (unsigned long long)S.c_rf);
-  atomicAdd(&s_stats[ST_DEPOSITS], (unsigned long long)S.c_cr + 1ull);  // one per cell left + the final one
-  atomicAdd(&s_stats[ST_LOOKUPS], (unsigned long long)S.c_lk);
+// Per-CTA statistics of a finished history.  Shared-memory 64-bit atomics are CAS loops on sm_100a, so the counters are
+// kept as {low, high} 32-bit words with native 32-bit adds and an explicit carry.
+__device__ __forceinline__ void stat_add32(uint32_t *s_stats, int which, uint32_t v) {
+  const uint32_t old = atomicAdd(&s_stats[2 * which], v);
+  if (old + v < old) atomicAdd(&s_stats[2 * which + 1], 1u);
 }
-
-struct WarpQueue {
-  uint64_t next, end;
-  bool exhausted;
-};
+__device__ __forceinline__ void stats_add(uint32_t *s_stats, const PState &S) {
+  stat_add32(s_stats, ST_EVENTS, events_of_finished(S));
+  stat_add32(s_stats, ST_SCATTERS, S.c_sc);
+  stat_add32(s_stats, ST_CROSSINGS, S.c_cr);
+  stat_add32(s_stats, ST_REFLECTIONS, S.c_rf);
+  stat_add32(s_stats, ST_DEPOSITS, S.c_cr + 1u);  // one per cell left + the final one
+  stat_add32(s_stats, ST_LOOKUPS, S.c_lk);
+}
+__device__ __forceinline__ void stats_flush(const uint32_t *s_stats, unsigned long long *g_stats) {
+  if (threadIdx.x < 6) {
+    const unsigned long long v = ((unsigned long long)s_stats[2 * threadIdx.x + 1] << 32) | s_stats[2 * threadIdx.x];
+    if (v) atomicAdd(&g_stats[threadIdx.x], v);
+  }
+}
 
 #ifndef BG_MIN_BLOCKS
 #define BG_MIN_BLOCKS 4
@@ -301,8 +340,8 @@ struct WarpQueue {
 template <int MODE, bool COUNTERS, bool SMEM, bool RESUME>
 __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const TransportParams P) {
   extern __shared__ double s_faces[];
-  __shared__ unsigned long long s_stats[6];
-  if (threadIdx.x < 6) s_stats[threadIdx.x] = 0ull;
+  __shared__ uint32_t s_stats[12];
+  if (threadIdx.x < 12) s_stats[threadIdx.x] = 0u;
   const double *faces;
   if (SMEM) {
     for (uint32_t t = threadIdx.x; t < P.mesh.n_faces; t += blockDim.x) s_faces[t] = P.mesh.faces[t];
@@ -323,8 +362,11 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   const unsigned FULL = 0xffffffffu;
   const unsigned lane_id = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane_id) - 1u;
+  const uint32_t n_total = (uint32_t)P.n;
 
-  WarpQueue q{0, 0, false};
+  // the warp's chunk of the work list [q_next, q_end); both are warp-uniform
+  uint32_t q_next = 0, q_end = 0;
+  bool exhausted = false;
   bool active = false;
   bool pending_scatter = false;
   PState S;
@@ -334,11 +376,10 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   S.i = S.j = S.k = 0;
   S.f = S.sig_a = S.sig_s = S.loc_abs = S.loc_trk = 0.0;
   S.surface = 0;
-  S.c_ev = S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
+  S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
-  S.need_f = S.need_xs = S.need_p = false;
   S.p_grp = 0.0;
-  uint64_t my_idx = 0;
+  uint32_t my_idx = 0;
   uint32_t ndep = 0;
   uint64_t dep_pos = 0;
 
@@ -357,61 +398,52 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
 
   for (;;) {
     // ---------------- refill idle lanes ----------------
-    unsigned need = __ballot_sync(FULL, !active);
-    if (need) {
-      bool want = !active;
-      while (!q.exhausted) {
-        if (q.next == q.end) {
-          unsigned long long base = 0;
-          if (lane_id == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
-          base = __shfl_sync(FULL, base, 0);
-          if (base >= P.n) {
-            q.exhausted = true;
-            break;
-          }
-          q.next = base;
-          q.end = (base + P.chunk < P.n) ? base + P.chunk : P.n;
+    // One attempt per trip and no inner loop: if the warp's chunk holds fewer photons than there are idle lanes, the
+    // lanes left over stay idle for this trip and are served from the next chunk on the next one (once per chunk).
+    const unsigned idle = __ballot_sync(FULL, !active);
+    if (idle) {
+      if (!exhausted && q_next == q_end) {
+        unsigned long long base = 0;
+        if (lane_id == 0) base = atomicAdd(P.work_counter, (unsigned long long)P.chunk);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= (unsigned long long)n_total) {
+          exhausted = true;
+        } else {
+          q_next = (uint32_t)base;
+          q_end = ((unsigned long long)n_total - base < P.chunk) ? n_total : (uint32_t)base + P.chunk;
         }
-        const unsigned m = __ballot_sync(FULL, want);
-        if (!m) break;
-        const uint64_t avail = q.end - q.next;
-        const unsigned r = __popc(m & lt_mask);
-        if (want && r < avail) {
-          const uint64_t slot = q.next + r;
-          const uint64_t idx = RESUME ? (uint64_t)P.index_list[slot] : slot;
+      }
+      if (!exhausted) {
+        const uint32_t avail = q_end - q_next;
+        const uint32_t r = __popc(idle & lt_mask);
+        if (!active && r < avail) {
+          const uint32_t slot = q_next + r;
+          const uint32_t idx = RESUME ? P.index_list[slot] : slot;
           pstate_load(S, P.ph, idx, C);
           my_idx = idx;
           if (RESUME) {
             const double2 acc = P.carry_acc[idx];
             const uint4 cn = P.carry_cnt[idx];
             S.loc_abs = acc.x; S.loc_trk = acc.y;
-            S.c_ev = cn.x; S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
+            S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
             S.c_lk = P.carry_lk[idx];
             pending_scatter = P.resume_pending_scatter != 0;
           }
           ndep = 0;
           if (MODE == TM_LOG) dep_pos = P.dep_off[idx];
           active = true;
-          want = false;
         }
-        const uint64_t asked = (uint64_t)__popc(m);
-        q.next += (asked < avail) ? asked : avail;
-        if (asked <= avail) break;
+        const uint32_t asked = __popc(idle);
+        q_next += (asked < avail) ? asked : avail;
+      } else if (idle == FULL) {
+        break;  // nothing left to fetch and nobody is working
       }
-      if (!__any_sync(FULL, active)) break;
     }
     if (!active) continue;
 
     // ---------------- one event ----------------
     if (RESUME && pending_scatter) {
-      // the parked scatter needs this visit's cell data (sigma_s, f, sigma_a) before it can be sampled
-      S.f = __ldg(&C.f[S.cell]);
-      const uint64_t o = (uint64_t)S.cell * C.G + S.group;
-      S.sig_a = __ldg(&C.opa[o]);
-      S.sig_s = __ldg(&C.ops[o]);
-      S.need_f = false; S.need_xs = false;
-      S.gmask |= 1ull << (S.group & 63u);
-      scatter_event(S, C);
+      scatter_event(S, C);  // the parked scatter (pstate_load has fetched this visit's f, sigma_a, sigma_s)
       pending_scatter = false;
     }
     uint8_t descriptor = EV_PASS;
@@ -421,14 +453,15 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
     } else if (r == R_DONE) {
       close_visit(S);
       if (MODE != TM_COUNT) stats_add(s_stats, S);
-      const uint64_t idx = my_idx;
+      const uint32_t idx = my_idx;
       if (MODE == TM_COUNT) {
         P.ndep[idx] = ndep;
       } else {
         P.desc[idx] = descriptor;
         P.ph.ee[idx] = make_double2(S.E, S.E0);
         if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
-        if (COUNTERS) reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(S.c_ev, S.c_sc, S.c_cr, S.c_rf);
+        if (COUNTERS)
+          reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(events_of_finished(S), S.c_sc, S.c_cr, S.c_rf);
       }
       active = false;
     }
@@ -436,7 +469,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
 
   // ---------------- statistics: one global atomic per CTA and counter ----------------
   __syncthreads();
-  if (MODE != TM_COUNT && threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  if (MODE != TM_COUNT) stats_flush(s_stats, P.stats);
 }
 
 }  // namespace bg

@@ -14,7 +14,7 @@ import numpy as np
 from . import gpu
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbranson_host.so")
+LIB_PATH = os.path.join(gpu.LIB_DIR, "libbranson_host.so")
 
 EXPORTS = ["bhost_create", "bhost_destroy", "bhost_last_error", "bhost_finished", "bhost_calculate_photon_energy",
            "bhost_cycle", "bhost_next_time_step", "bhost_get_array", "bhost_get_param", "bhost_gpu_ctx", "bhost_total_transport_time"]

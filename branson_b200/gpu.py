@@ -11,8 +11,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# BRANSON_GPU_LIB: developer knob to load an experimental build of the same ABI (tools/, never the tests or bench)
-LIB_PATH = os.environ.get("BRANSON_GPU_LIB") or os.path.join(_HERE, "libbranson_gpu.so")
+# BRANSON_LIB_DIR: developer knob to load an experimental build of the same ABI (both libraries, built with
+# `make -C branson_b200/csrc OUT=<dir> EXTRA=...`) for A/B timing; the tests and the bench use the in-tree build
+LIB_DIR = os.environ.get("BRANSON_LIB_DIR") or _HERE
+LIB_PATH = os.path.join(LIB_DIR, "libbranson_gpu.so")
 
 ABI_VERSION = 1
 HISTORY, EVENT = 0, 1
@@ -55,7 +57,7 @@ EXPORTS = [
     "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
-    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
 ]
 
 
@@ -94,6 +96,7 @@ def lib():
         L.bgpu_set_group_walk.argtypes = [vp, i32]
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
         L.bgpu_test_threefry.argtypes = [vp, vp]
+        L.bgpu_test_fastmath.argtypes = [C.c_int, u64, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -274,3 +277,13 @@ def threefry(ctr, key):
     if lib().bgpu_test_threefry(_ptr(ck), _ptr(out)):
         raise GpuError("bgpu_test_threefry failed")
     return int(out[0]), int(out[1])
+
+
+def fastmath(which, x):
+    """csrc/fastmath.cuh on the device: which = "exp" | "log" | "sincos" | "cuda_sincos" (the last: libdevice)."""
+    x = np.ascontiguousarray(x, np.float64)
+    out, out2 = np.zeros_like(x), np.zeros_like(x)
+    code = {"exp": 0, "log": 1, "sincos": 2, "cuda_sincos": 3}[which]
+    if lib().bgpu_test_fastmath(code, x.size, _ptr(x), _ptr(out), _ptr(out2)):
+        raise GpuError("bgpu_test_fastmath failed")
+    return (out, out2) if code >= 2 else out

@@ -168,6 +168,10 @@ int bgpu_set_group_walk(bgpu_ctx *ctx, int closed_form);
  * of {ctr0, ctr1, key0, key1}, src/random123/threefry.h:196-282) */
 int bgpu_test_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *out);
 int bgpu_test_threefry(const uint64_t ctr_key[4], uint64_t out[2]);
+/* accuracy hook for the loop's own log / exp / sincos (csrc/fastmath.cuh; they stand in for the libm calls of
+ * src/history_based_transport.h:63,74 and src/sampling_functions.h:66-68): which = 0 exp, 1 log (positive normal
+ * arguments), 2 sincos (out = sin, out2 = cos), 3 CUDA's own sincos for comparison */
+int bgpu_test_fastmath(int which, uint64_t n, const double *in, double *out, double *out2);
 
 #ifdef __cplusplus
 }

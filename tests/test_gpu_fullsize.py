@@ -19,7 +19,7 @@ def _run(deck, tmp_path, cycles, **kw):
     return reps, arrays
 
 
-def _check_balance(reps):
+def _check_balance(reps, n_cells):
     for r in reps:
         g = r["gpu"]
         assert g["n_transported"] == g["n_killed"] + g["n_exit"] + g["n_census"]
@@ -28,19 +28,24 @@ def _check_balance(reps):
         total = r["pre_census_E"] + r["emission_E"] + r["source_E"]
         # exact balance of what the device made, tallied and kept: 1e-12 (north_star)
         assert abs(r["rad_balance_exact"]) <= 1e-12 * total, (r["step"], r["rad_balance_exact"], total)
-        # the reference's own residual formula sums abs_E serially over the cells and drops sub-ulp addends
-        # (src/mesh.h:359; measured 1.5e-12 on the 591 500-cell hohlraum, tools/debug_conservation.py)
-        assert abs(r["rad_conservation"]) <= 1e-11 * total, (r["step"], r["rad_conservation"], total)
-        # material residual, same serial-sum caveat; its scale is the energy the cycle moved through the material
+        # the reference's own residual formulas (src/imc_state.h:254-258) are built from serial double sums over the
+        # cells (abs_E src/mesh.h:359, post_mat_E :327-362), which carry up to n_cells half-ulps of their partial sums:
+        # 6.6e-11 relative at 591 500 cells (observed 1.5e-12 radiation / 1.5e-11 material), 8.9e-10 at 200^3 (observed
+        # 1.6e-10); the exact fsum balance of the same numbers is 0 (tools/debug_conservation.py).  The host layer
+        # reproduces the reference's sums bit for bit (tests/test_host_logic.py), so the unmodified reference shows
+        # the same residuals; 1e-12 holds on the small meshes.
+        ref_tol = max(1e-12, n_cells * 2.0 ** -53)
+        assert abs(r["rad_conservation"]) <= ref_tol * total, (r["step"], r["rad_conservation"], total)
+        # material residual: its scale is the energy the cycle moved through the material
         mat_scale = abs(r["pre_mat_E"]) + abs(r["absorbed_E"]) + abs(r["emission_E"])
-        assert abs(r["mat_conservation"]) <= 1e-11 * mat_scale, (r["step"], r["mat_conservation"], mat_scale)
+        assert abs(r["mat_conservation"]) <= ref_tol * mat_scale, (r["step"], r["mat_conservation"], mat_scale)
 
 
 def test_hohlraum_single_node_full_size(tmp_path):
     # configs[2]: 65 x 65 x 140 cells, 30 groups, 1e7 photons (reference inputs/3D_hohlraum_single_node.xml)
     deck = decks.hohlraum_single(t_stop=0.02)
     reps, arr = _run(deck, tmp_path, 2)
-    _check_balance(reps)
+    _check_balance(reps, 65 * 65 * 140)
     assert reps[0]["gpu"]["n_transported"] > 1.0e7
     # the deterministic mode sees the same photons (identical integer bookkeeping) and the same tallies to rounding
     reps_d, arr_d = _run(deck, tmp_path, 1, tally_mode=gpu.TALLY_DETERMINISTIC)
@@ -55,17 +60,17 @@ def test_hohlraum_single_node_full_size(tmp_path):
 def test_hot_zone_full_size(tmp_path):
     # configs[1]: 200 x 200 x 1 cells, gray, 1e6 photons (reference inputs/hot_zone_input.xml)
     reps, _ = _run(decks.hot_zone(t_stop=0.05), tmp_path, 5)
-    _check_balance(reps)
+    _check_balance(reps, 200 * 200)
 
 
 def test_marshak_wave_full_size(tmp_path):
     # configs[0]: 25 cells, T-dependent opacity, SOURCE face, 1e6 photons
     reps, _ = _run(decks.marshak_wave(t_stop=0.05), tmp_path, 5)
-    _check_balance(reps)
+    _check_balance(reps, 25)
     assert all(r["source_E"] > 0 for r in reps)
 
 
 def test_big_cube_scaled(tmp_path):
     # configs[4] scaled to one GPU: 200^3 cells, 2e7 photons per cycle
     reps, _ = _run(decks.big_cube(n=200, photons=20_000_000, t_stop=0.002), tmp_path, 2)
-    _check_balance(reps)
+    _check_balance(reps, 200 ** 3)

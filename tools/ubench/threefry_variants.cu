@@ -33,8 +33,32 @@ __device__ __forceinline__ uint64_t rotxor_mul(uint64_t x1, uint64_t x0) {
   return pack(nlo, nhi);
 }
 
+// 64-bit add on the fma pipe: IMAD.WIDE.U32 (x1.lo * one + x0) then the high word; `one` is a run-time 1 so that
+// ptxas cannot fold the multiply back into IADD3 (alu pipe)
+__device__ uint32_t g_one;
+__device__ __forceinline__ uint64_t add_wide(uint64_t x0, uint64_t x1) {
+  const uint32_t one = g_one;
+  uint64_t t;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"((uint32_t)x1), "r"(one), "l"(x0));
+  uint32_t hi = (uint32_t)(t >> 32), add = (uint32_t)(x1 >> 32);
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(add), "r"(one), "r"(hi));
+  return pack((uint32_t)t, hi);
+}
+
 template <int V, int R>
 __device__ __forceinline__ void tf_round(uint64_t &x0, uint64_t &x1) {
+  if (V == 4) { x0 = add_wide(x0, x1); x1 = rotl_fs<R>(x1); x1 ^= x0; return; }
+  if (V == 5) { x0 = add_wide(x0, x1); x1 = rotxor_mul<R>(x1, x0); return; }
+  if (V == 6) {  // B / C alternating
+    if (R == 16 || R == 12 || R == 24 || R == 42) { x0 += x1; x1 = rotxor_mul<R>(x1, x0); }
+    else { x0 = add_wide(x0, x1); x1 = rotl_fs<R>(x1); x1 ^= x0; }
+    return;
+  }
+  if (V == 7) {  // A / B alternating
+    if (R == 16 || R == 12 || R == 24 || R == 42) { x0 += x1; } else { x0 = add_wide(x0, x1); }
+    x1 = rotl_fs<R>(x1); x1 ^= x0;
+    return;
+  }
   x0 += x1;
   if (V == 0) { x1 = rotl_plain(x1, R); x1 ^= x0; }
   else if (V == 1) { x1 = rotl_fs<R>(x1); x1 ^= x0; }
@@ -113,6 +137,7 @@ static void run(const char *name, int blocks_per_sm, uint64_t *d_out, uint64_t *
 }
 
 int main() {
+  { uint32_t one = 1; cudaMemcpyToSymbol(g_one, &one, sizeof one); }
   uint64_t *d_out; cudaMalloc(&d_out, 148 * 16 * 128 * sizeof(uint64_t));
   uint64_t ref[4] = {0, 0, 0, 0};
   for (int bps : {4, 8}) {
@@ -122,6 +147,10 @@ int main() {
     run<2, 4>("V2 mulwide", bps, d_out, ref); run<3, 4>("V3 mixed", bps, d_out, ref);
     run<1, 5>("V1 funnel", bps, d_out, ref); run<3, 5>("V3 mixed", bps, d_out, ref);
     run<1, 8>("V1 funnel", bps, d_out, ref); run<3, 8>("V3 mixed", bps, d_out, ref);
+    run<4, 1>("V4 wideadd+funnel", bps, d_out, ref); run<4, 4>("V4 wideadd+funnel", bps, d_out, ref);
+    run<5, 1>("V5 wideadd+mulrot", bps, d_out, ref); run<5, 4>("V5 wideadd+mulrot", bps, d_out, ref);
+    run<6, 1>("V6 B/C alt", bps, d_out, ref); run<6, 4>("V6 B/C alt", bps, d_out, ref);
+    run<7, 1>("V7 A/B alt", bps, d_out, ref); run<7, 4>("V7 A/B alt", bps, d_out, ref);
   }
   return 0;
 }
