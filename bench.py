@@ -44,6 +44,9 @@ DT = 0.01
 METRIC = "photon histories/sec (3D hohlraum, 30 groups, replicated)"
 UNIT = "histories/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+# Threefry2x64-20 alone on all 148 SMs (tools/ubench/threefry_variants.cu, best formulation, measured on this pool's
+# B200: profiles/threefry_ubench_r01.txt): the alu-pipe ceiling of the draws the reference's algorithm prescribes
+THREEFRY_PEAK_GDRAWS = 181.5
 
 
 def make_deck(n_gpus: int, cycles: int, photons_per_gpu: int = PHOTONS_PER_GPU, threads: int = 1):
@@ -313,8 +316,18 @@ def our_arm(args):
                              "kernel_histories_per_s": hist / (tr_ms * 1e-3),
                              "events_per_history": sum(x["n_events"] for x in g) / hist,
                              "scatters_per_history": sum(x["n_scatters"] for x in g) / hist,
-                             "note": "scattering-dominated cycles are INT32/FP64-pipe bound (Threefry + log/exp/sincos), "
-                                     "see DESIGN.md section 5 and profiles/"},
+                             "note": "scattering-dominated cycles are alu-pipe bound (Threefry), not HBM bound: see "
+                                     "compute_bound below, DESIGN.md section 5 and profiles/"},
+                # what actually limits the kernel on this workload (ncu: alu pipe 70 %, DRAM 1 %): the Threefry draws the
+                # reference's algorithm prescribes (1 per event + 4 per scatter; exact for decks with sigma_s = 0 and
+                # f < 1, i.e. all of BASELINE's) against a kernel that does nothing but Threefry
+                "compute_bound": {"bound": "alu pipe (Threefry2x64-20 draws)",
+                                  "achieved": sum(x["n_events"] + 4 * x["n_scatters"] for x in g) / (tr_ms * 1e-3) / 1e9,
+                                  "peak": THREEFRY_PEAK_GDRAWS, "unit": "Gdraws/s",
+                                  "frac": sum(x["n_events"] + 4 * x["n_scatters"] for x in g) / (tr_ms * 1e-3) / 1e9
+                                  / THREEFRY_PEAK_GDRAWS,
+                                  "peak_source": "tools/ubench/threefry_variants.cu on this pool's B200 "
+                                                 "(profiles/threefry_ubench_r01.txt)"},
                 "clocks": clocks,
                 "conservation": {"max_rel_radiation_balance": max(
                     abs(r["rad_balance_exact"]) / (r["pre_census_E"] + r["emission_E"] + r["source_E"]) for r in reps)}}

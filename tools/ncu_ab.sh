@@ -11,7 +11,7 @@ import csv, sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
 h = rows[0]; i_n = h.index("Metric Name"); i_v = h.index("Metric Value")
 d = {r[i_n]: r[i_v] for r in rows[1:]}
-st = {k.replace("smsp__pcsamp_warps_issue_stalled_", ""): float(v.replace(",", "")) for k, v in d.items() if "pcsamp" in k}
+st = {k.replace("smsp__pcsamp_warps_issue_stalled_", ""): float(v.replace(",", "")) for k, v in d.items() if "pcsamp" in k and v != "n/a"}
 tot = sum(st.values()) or 1
 for k, v in d.items():
     if "pcsamp" not in k: print(f"  {k}: {v}")

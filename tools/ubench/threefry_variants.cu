@@ -45,8 +45,36 @@ __device__ __forceinline__ uint64_t add_wide(uint64_t x0, uint64_t x1) {
   return pack((uint32_t)t, hi);
 }
 
+// rotl + xor with ONE 32-bit half formed on the fma pipe: (hi << S) | (lo >> (32 - S)) = hi * 2^S + mulhi(lo, 2^S),
+// the multiplier 2^S read from constant memory so that ptxas cannot turn the multiplies back into alu-pipe shifts
+__constant__ uint32_t c_pow[32];
+template <int R, int HALVES>
+__device__ __forceinline__ uint64_t rotxor_imad(uint64_t x1, uint64_t x0) {
+  uint32_t lo = (uint32_t)x1, hi = (uint32_t)(x1 >> 32);
+  if (R == 32) return pack(hi, lo) ^ x0;
+  if (R > 32) { uint32_t t = lo; lo = hi; hi = t; }
+  constexpr int S = R & 31;
+  const uint32_t c = c_pow[S];
+  uint32_t nhi, nlo;
+  {
+    uint32_t t;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(lo), "r"(c));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nhi) : "r"(hi), "r"(c), "r"(t));
+  }
+  if (HALVES == 2) {
+    uint32_t t;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(hi), "r"(c));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nlo) : "r"(lo), "r"(c), "r"(t));
+  } else {
+    nlo = __funnelshift_l(hi, lo, S);
+  }
+  return pack(nlo ^ (uint32_t)x0, nhi ^ (uint32_t)(x0 >> 32));
+}
+
 template <int V, int R>
 __device__ __forceinline__ void tf_round(uint64_t &x0, uint64_t &x1) {
+  if (V == 8) { x0 += x1; x1 = rotxor_imad<R, 1>(x1, x0); return; }
+  if (V == 9) { x0 += x1; x1 = rotxor_imad<R, 2>(x1, x0); return; }
   if (V == 4) { x0 = add_wide(x0, x1); x1 = rotl_fs<R>(x1); x1 ^= x0; return; }
   if (V == 5) { x0 = add_wide(x0, x1); x1 = rotxor_mul<R>(x1, x0); return; }
   if (V == 6) {  // B / C alternating
@@ -138,6 +166,7 @@ static void run(const char *name, int blocks_per_sm, uint64_t *d_out, uint64_t *
 
 int main() {
   { uint32_t one = 1; cudaMemcpyToSymbol(g_one, &one, sizeof one); }
+  { uint32_t pw[32]; for (int i = 0; i < 32; ++i) pw[i] = 1u << i; cudaMemcpyToSymbol(c_pow, pw, sizeof pw); }
   uint64_t *d_out; cudaMalloc(&d_out, 148 * 16 * 128 * sizeof(uint64_t));
   uint64_t ref[4] = {0, 0, 0, 0};
   for (int bps : {4, 8}) {
@@ -151,6 +180,8 @@ int main() {
     run<5, 1>("V5 wideadd+mulrot", bps, d_out, ref); run<5, 4>("V5 wideadd+mulrot", bps, d_out, ref);
     run<6, 1>("V6 B/C alt", bps, d_out, ref); run<6, 4>("V6 B/C alt", bps, d_out, ref);
     run<7, 1>("V7 A/B alt", bps, d_out, ref); run<7, 4>("V7 A/B alt", bps, d_out, ref);
+    run<8, 1>("V8 one half imad", bps, d_out, ref); run<8, 4>("V8 one half imad", bps, d_out, ref);
+    run<9, 1>("V9 both halves imad", bps, d_out, ref); run<9, 4>("V9 both halves imad", bps, d_out, ref);
   }
   return 0;
 }
