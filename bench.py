@@ -253,8 +253,10 @@ def our_arm(args):
     deck = make_deck(world, cycles, photons_per_gpu=args.photons)
     tmp = tempfile.mkdtemp(prefix="branson_bench_")
     xml = deck.write(os.path.join(tmp, f"deck_rank{rank}.xml"))
+    on_device = args.mesh == "device"
     d = driver.Driver(xml, n_groups=N_GROUPS, rank=rank, n_ranks=world, device=local,
-                      algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, comm=comm)
+                      algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, comm=comm,
+                      mesh_on_device=on_device)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -262,18 +264,40 @@ def our_arm(args):
             torch.distributed.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    def step(drv, dev_mesh):
+        r = drv.cycle()
+        if dev_mesh:
+            drv.array("T_e")  # the cycle's result arrays live on the device in this mode: read one back every step
+        return r
+
     for _ in range(args.warmup):
-        d.cycle()
+        step(d, on_device)
     launches_before = d.gpu_context().stats()["n_launches"]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     sync_all()
     t0 = time.perf_counter()
-    reps = [d.cycle() for _ in range(args.steps)]
+    reps = [step(d, on_device) for _ in range(args.steps)]
     sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    # the same cycles through the array-exchanging path (host Mesh: f / op_a / op_s / E arrays up, tallies down)
+    wall_host = None
+    if on_device and not args.no_host_mesh_e2e:
+        d.close()
+        d2 = driver.Driver(xml, n_groups=N_GROUPS, rank=rank, n_ranks=world, device=local,
+                           algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, comm=comm,
+                           mesh_on_device=False)
+        for _ in range(args.warmup):
+            d2.cycle()
+        sync_all()
+        t0 = time.perf_counter()
+        reps_host = [d2.cycle() for _ in range(args.steps)]
+        sync_all()
+        wall_host = time.perf_counter() - t0
+        hist_host = sum(r["gpu"]["n_transported"] for r in reps_host)
+        d = d2
 
     g = [r["gpu"] for r in reps]
     dev_ms = sum(x["ms_source"] + x["ms_transport"] + x["ms_census"] for x in g)
@@ -281,32 +305,45 @@ def our_arm(args):
     hist = sum(x["n_transported"] for x in g)
     abytes = sum(algorithmic_bytes(x) for x in g)
     launches = g[-1]["n_launches"] - launches_before  # kernels launched through the ctx inside the timed region
-    vals = torch.tensor([dev_ms, wall, tr_ms, float(hist), float(abytes)], dtype=torch.float64, device=f"cuda:{local}")
+    vals = torch.tensor([dev_ms, wall, tr_ms, float(hist), float(abytes), wall_host or 0.0,
+                         float(hist_host) if wall_host else 0.0], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         mx = vals.clone()
         torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
         sm = vals.clone()
         torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM)
-        dev_ms_max, wall_max, tr_ms_max = mx[0].item(), mx[1].item(), mx[2].item()
-        hist_all = sm[3].item()
+        dev_ms_max, wall_max, tr_ms_max, wall_host_max = mx[0].item(), mx[1].item(), mx[2].item(), mx[5].item()
+        hist_all, hist_host_all = sm[3].item(), sm[6].item()
     else:
         dev_ms_max, wall_max, tr_ms_max, hist_all = dev_ms, wall, tr_ms, float(hist)
+        wall_host_max, hist_host_all = wall_host or 0.0, float(hist_host) if wall_host else 0.0
 
     if rank == 0:
         n_cells = int(d.param("n_cells"))
         peak, peak_src = measured_peak()
         achieved = abytes / (tr_ms * 1e-3) / 1e9  # rank 0's kernel: bytes per launch / its average duration
-        h2d = 5 * n_cells * 8  # f, op_a, op_s, E_emission, E_source
-        d2h = 2 * n_cells * 8 + 256
+        h2d_host = 5 * n_cells * 8  # f, op_a, op_s, E_emission, E_source
+        d2h_host = 2 * n_cells * 8 + 256
+        # device mesh: (dt, step, total_E) in, the running sums and cycle statistics out, plus the T_e read-back
+        h2d, d2h = (64, 8 * 16 + 256 + 8 * n_cells) if on_device else (h2d_host, d2h_host)
         line = {"metric": METRIC, "value": hist_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(world, args.photons),
                 "e2e": {"value": hist_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * wall_max / args.steps,
+                        "path": ("Driver.cycle() with the mesh physics on the device (bgpu_mesh_*): cell state resident "
+                                 "in HBM, scalars in, sums + T_e array out every cycle" if on_device else
+                                 "Driver.cycle() with the host Mesh: f/op_a/op_s/E arrays uploaded, tallies downloaded "
+                                 "every cycle"),
                         "host_phase_ms_per_step": {k[2:]: 1e3 * sum(r[k] for r in reps) / args.steps for k in
                                                    ("t_calc_energy", "t_cell_upload", "t_source", "t_transport",
                                                     "t_allreduce", "t_tally_download", "t_update_T")}},
+                "e2e_host_mesh": ({"value": hist_host_all / wall_host_max, "unit": UNIT,
+                                   "h2d_bytes_per_step": h2d_host, "d2h_bytes_per_step": d2h_host,
+                                   "ms_per_step": 1e3 * wall_host_max / args.steps,
+                                   "path": "the same cycles with the host Mesh (bit-identical host physics; arrays cross "
+                                           "PCIe both ways every cycle)"} if wall_host else None),
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "k_transport_history", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -354,6 +391,9 @@ def main():
     ap.add_argument("--photons", type=int, default=PHOTONS_PER_GPU, help="user photons per cycle per GPU")
     ap.add_argument("--algorithm", default="history", choices=["history", "event"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mesh", default="device", choices=["device", "host"],
+                    help="where calculate_photon_energy / update_temperature run (e2e path)")
+    ap.add_argument("--no-host-mesh-e2e", action="store_true", help="skip the second, host-mesh e2e measurement")
     ap.add_argument("--cpu-sample-photons", type=int, default=1_000_000)
     ap.add_argument("--ref-photons", type=int, default=400_000,
                     help="--impl reference: user photons per cycle of the bounded sample")

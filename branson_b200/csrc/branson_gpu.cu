@@ -17,6 +17,7 @@
 #include "census.cuh"
 #include "common.cuh"
 #include "event.cuh"
+#include "mesh_dev.cuh"
 #include "source.cuh"
 #include "transport.cuh"
 
@@ -83,6 +84,17 @@ struct bgpu_ctx {
   uint32_t chunk = 128;
   uint64_t event_tail = 0;   // active-list size below which BGPU_EVENT hands over to the history kernel (0: auto)
   uint32_t event_passes = 0;
+
+  // device-resident mesh physics (bgpu_mesh_*, mesh_dev.cuh); allocated by bgpu_mesh_init
+  bool mesh_ready = false;
+  RegionDev *d_regions = nullptr;
+  uint32_t *d_region_of_cell = nullptr;
+  double *d_mesh = nullptr;  // n_cells doubles each: T_e, T_r0, T_s, T_r, op_a, op_s, E_emission, E_source, E_census, E_emission_global
+  double *d_tile_sums = nullptr, *d_mesh_sums = nullptr;
+  uint32_t mesh_tiles = 0;
+  double mesh_dt = 0.0;
+  uint32_t mesh_step = 0;
+  bool mesh_redistributed = false;
 
   uint64_t launches = 0;  // kernels launched through this ctx since creation
   bgpu_cycle_stats stats{};
@@ -686,7 +698,8 @@ void bgpu_destroy(bgpu_ctx *c) {
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
-                  c->d_results, c->work.base, c->census.base, c->d_desc, c->d_counters};
+                  c->d_results, c->work.base, c->census.base, c->d_desc, c->d_counters, c->d_regions,
+                  c->d_region_of_cell, c->d_mesh, c->d_tile_sums, c->d_mesh_sums};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -731,28 +744,28 @@ int bgpu_set_cell_groups(bgpu_ctx *c, const double *f, const double *abs_groups,
   return 0;
 }
 
-int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission, const double *E_source,
-                const double *E_census, double total_E, uint64_t *n_new_out, uint64_t *n_total_out) {
-  if (!c || !E_emission || !E_source) return fail(c, "bgpu_source: null argument");
-  CU(c, cudaSetDevice(c->device));
+}  // extern "C"
+
+namespace {
+// make_photons / make_initial_census_photons / join_photon_arrays from per-cell energies that are already on the
+// device (ev[0] has been recorded by the caller)
+int source_from_device(bgpu_ctx *c, uint32_t cycle, double dt, const double *dE_emission, const double *dE_source,
+                       const double *dE_census /* nullptr unless cycle 1 */, double total_E, uint64_t *n_new_out,
+                       uint64_t *n_total_out) {
   const uint32_t nc = c->mesh.n_cells;
-  double *dE = c->d_cell_stage;
-  CU(c, cudaMemcpyAsync(dE, E_emission, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(dE + nc, E_source, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
-  if (E_census) CU(c, cudaMemcpyAsync(dE + 2ull * nc, E_census, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaEventRecord(c->ev[0], c->stream));  // inputs are resident from here on
+  const double *E_census = dE_census;
   if (ensure(c, c->scr_counts, 4ull * 3 * nc)) return 1;
   if (ensure(c, c->scr_offsets, 8ull * (3ull * nc + 2))) return 1;
   uint32_t *cnt2 = (uint32_t *)c->scr_counts.p, *cnt1 = cnt2 + 2ull * nc;
   uint64_t *off2 = (uint64_t *)c->scr_offsets.p, *off1 = off2 + 2ull * nc + 1;
   ++c->launches;
-  k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 2, dE, dE + nc, c->n_user, total_E, cnt2);
+  k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 2, dE_emission, dE_source, c->n_user, total_E, cnt2);
   if (device_scan(c, cnt2, 2ull * nc, off2)) return 1;
   uint64_t n_new = 0, n_init = 0;
   CU(c, cudaMemcpyAsync(&n_new, off2 + 2ull * nc, 8, cudaMemcpyDeviceToHost, c->stream));
   if (E_census) {
     ++c->launches;
-    k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 1, dE + 2ull * nc, nullptr, c->n_user, total_E, cnt1);
+    k_source_count<<<grid_for(nc, 256), 256, 0, c->stream>>>(nc, 1, dE_census, nullptr, c->n_user, total_E, cnt1);
     if (device_scan(c, cnt1, nc, off1)) return 1;
     CU(c, cudaMemcpyAsync(&n_init, off1 + nc, 8, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -773,8 +786,8 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
     S.offsets = off2;
     S.n_entries = 2 * nc;
     S.kinds = 2;
-    S.E0 = dE;
-    S.E1 = dE + nc;
+    S.E0 = dE_emission;
+    S.E1 = dE_source;
     // src/source.h:221-222
     S.stream_base = 10000000000000ULL * (uint64_t)cycle + c->n_user * (uint64_t)c->rank;
     ++c->launches;
@@ -787,7 +800,7 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
       S.offsets = off1;
       S.n_entries = nc;
       S.kinds = 1;
-      S.E0 = dE + 2ull * nc;
+      S.E0 = dE_census;
       S.E1 = nullptr;
       S.stream_base = c->n_user * (uint64_t)c->rank;  // src/source.h:144
       ++c->launches;
@@ -814,6 +827,196 @@ int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission
   CU(c, cudaEventElapsedTime(&c->stats.ms_source, c->ev[0], c->ev[1]));
   if (n_new_out) *n_new_out = n_new;
   if (n_total_out) *n_total_out = n_total;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int bgpu_source(bgpu_ctx *c, uint32_t cycle, double dt, const double *E_emission, const double *E_source,
+                const double *E_census, double total_E, uint64_t *n_new_out, uint64_t *n_total_out) {
+  if (!c || !E_emission || !E_source) return fail(c, "bgpu_source: null argument");
+  CU(c, cudaSetDevice(c->device));
+  const uint32_t nc = c->mesh.n_cells;
+  double *dE = c->d_cell_stage;
+  CU(c, cudaMemcpyAsync(dE, E_emission, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(dE + nc, E_source, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  if (E_census) CU(c, cudaMemcpyAsync(dE + 2ull * nc, E_census, 8ull * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->ev[0], c->stream));  // inputs are resident from here on
+  return source_from_device(c, cycle, dt, dE, dE + nc, E_census ? dE + 2ull * nc : nullptr, total_E, n_new_out,
+                            n_total_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-resident mesh physics (mesh_dev.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+enum : int { MA_T_E = 0, MA_T_R0, MA_T_S, MA_T_R, MA_OP_A, MA_OP_S, MA_E_EMISSION, MA_E_SOURCE, MA_E_CENSUS, MA_E_EMISSION_GLOBAL, MA_N };
+inline double *mesh_arr(bgpu_ctx *c, int which) { return c->d_mesh + (uint64_t)which * c->mesh.n_cells; }
+
+MeshPhysParams mesh_params(bgpu_ctx *c) {
+  MeshPhysParams P{};
+  P.mesh = c->mesh;
+  P.regions = c->d_regions;
+  P.region_of_cell = c->d_region_of_cell;
+  P.T_e = mesh_arr(c, MA_T_E);
+  P.T_r0 = mesh_arr(c, MA_T_R0);
+  P.T_s = mesh_arr(c, MA_T_S);
+  P.T_r = mesh_arr(c, MA_T_R);
+  P.f = c->d_f;
+  P.op_a = mesh_arr(c, MA_OP_A);
+  P.op_s = mesh_arr(c, MA_OP_S);
+  P.E_emission = mesh_arr(c, MA_E_EMISSION);
+  P.E_source = mesh_arr(c, MA_E_SOURCE);
+  P.E_census = mesh_arr(c, MA_E_CENSUS);
+  P.E_emission_global = mesh_arr(c, MA_E_EMISSION_GLOBAL);
+  P.tally = (double2 *)c->d_tally;
+  P.tile_sums = c->d_tile_sums;
+  P.n_tiles = c->mesh_tiles;
+  P.dt = c->mesh_dt;
+  P.replicated_factor = 1.0 / static_cast<double>(c->n_ranks);  // src/mesh.h:87
+  P.n_user = (uint64_t)(uint32_t)c->n_user;  // the reference passes n_user_photons as uint32_t here (src/mesh.h:237)
+  P.step = c->mesh_step;
+  P.rank = c->rank;
+  P.n_ranks = c->n_ranks;
+  return P;
+}
+
+int mesh_fetch_sums(bgpu_ctx *c, uint32_t q_mask, bgpu_mesh_sums *out) {
+  ++c->launches;
+  k_mesh_final_sums<<<1, 32, 0, c->stream>>>(c->d_tile_sums, c->mesh_tiles, q_mask, c->d_mesh_sums);
+  CU(c, cudaGetLastError());
+  double h[MS_N];
+  CU(c, cudaMemcpyAsync(h, c->d_mesh_sums, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (q_mask & (1u << MS_PRE_MAT)) out->pre_mat_E = h[MS_PRE_MAT];
+  if (q_mask & (1u << MS_EMISSION)) out->emission_E = h[MS_EMISSION];
+  if (q_mask & (1u << MS_CENSUS)) out->census_E = h[MS_CENSUS];
+  if (q_mask & (1u << MS_SOURCE)) out->source_E = h[MS_SOURCE];
+  if (q_mask & (1u << MS_TOTAL)) out->total_photon_E = h[MS_TOTAL];
+  if (q_mask & (1u << MS_ABS)) out->absorbed_E = h[MS_ABS];
+  if (q_mask & (1u << MS_POST_MAT)) out->post_mat_E = h[MS_POST_MAT];
+  return 0;
+}
+}  // namespace
+
+int bgpu_mesh_init(bgpu_ctx *c, uint32_t n_regions, const bgpu_region *regions, const uint32_t *region_of_cell,
+                   const double *T_e, const double *T_r, const double *T_s) {
+  if (!c || !n_regions || !regions || !region_of_cell || !T_e || !T_r || !T_s)
+    return fail(c, "bgpu_mesh_init: null argument");
+  static_assert(sizeof(bgpu_region) == sizeof(RegionDev), "bgpu_region layout");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells;
+  for (uint64_t i = 0; i < nc; ++i)
+    if (region_of_cell[i] >= n_regions) return fail(c, "bgpu_mesh_init: cell %llu names region %u of %u",
+                                                    (unsigned long long)i, region_of_cell[i], n_regions);
+  if (!c->d_mesh) {
+    c->mesh_tiles = (uint32_t)((nc + MESH_TILE - 1) / MESH_TILE);
+    CU(c, cudaMalloc((void **)&c->d_region_of_cell, 4 * nc));
+    CU(c, cudaMalloc((void **)&c->d_mesh, 8 * nc * MA_N));
+    CU(c, cudaMalloc((void **)&c->d_tile_sums, 8ull * MS_N * c->mesh_tiles));
+    CU(c, cudaMalloc((void **)&c->d_mesh_sums, 8 * MS_N));
+  }
+  if (c->d_regions) CU(c, cudaFree(c->d_regions));
+  CU(c, cudaMalloc((void **)&c->d_regions, sizeof(RegionDev) * n_regions));
+  CU(c, cudaMemcpyAsync(c->d_regions, regions, sizeof(RegionDev) * n_regions, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_region_of_cell, region_of_cell, 4 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_mesh, 0, 8 * nc * MA_N, c->stream));
+  CU(c, cudaMemcpyAsync(mesh_arr(c, MA_T_E), T_e, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(mesh_arr(c, MA_T_R0), T_r, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(mesh_arr(c, MA_T_S), T_s, 8 * nc, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->mesh_ready = true;
+  return 0;
+}
+
+int bgpu_mesh_calculate_photon_energy(bgpu_ctx *c, double dt, uint32_t step, bgpu_mesh_sums *sums) {
+  if (!c || !sums) return fail(c, "bgpu_mesh_calculate_photon_energy: null argument");
+  if (!c->mesh_ready) return fail(c, "bgpu_mesh_calculate_photon_energy: call bgpu_mesh_init first");
+  CU(c, cudaSetDevice(c->device));
+  c->mesh_dt = dt;
+  c->mesh_step = step;
+  c->mesh_redistributed = false;
+  const MeshPhysParams P = mesh_params(c);
+  ++c->launches;
+  k_mesh_energy<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(P);
+  // every group gets the cell's gray opacity (Cell::set_op_a / set_op_s, src/cell.h:260-275)
+  ++c->launches;
+  k_expand_groups<<<grid_for((uint64_t)c->mesh.n_cells * c->mesh.G, 256), 256, 0, c->stream>>>(
+      c->mesh.n_cells, c->mesh.G, P.op_a, P.op_s, c->d_opa, c->d_ops);
+  CU(c, cudaGetLastError());
+  c->have_cell_data = true;
+  c->uniform_groups = true;
+  *sums = bgpu_mesh_sums{};
+  return mesh_fetch_sums(c, (1u << MS_PRE_MAT) | (1u << MS_EMISSION) | (1u << MS_CENSUS) | (1u << MS_SOURCE) |
+                                (1u << MS_TOTAL), sums);
+}
+
+int bgpu_mesh_redistribute(bgpu_ctx *c, double global_source_E, bgpu_mesh_sums *sums) {
+  if (!c || !sums) return fail(c, "bgpu_mesh_redistribute: null argument");
+  if (!c->mesh_ready) return fail(c, "bgpu_mesh_redistribute: call bgpu_mesh_init first");
+  CU(c, cudaSetDevice(c->device));
+  MeshPhysParams P = mesh_params(c);
+  P.global_source_E = global_source_E;
+  ++c->launches;
+  k_mesh_redistribute<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(P);
+  CU(c, cudaGetLastError());
+  c->mesh_redistributed = true;
+  return mesh_fetch_sums(c, (1u << MS_EMISSION) | (1u << MS_CENSUS) | (1u << MS_SOURCE) | (1u << MS_TOTAL), sums);
+}
+
+int bgpu_mesh_source(bgpu_ctx *c, uint32_t cycle, double total_E, uint64_t *n_new_out, uint64_t *n_total_out) {
+  if (!c) return fail(c, "bgpu_mesh_source: null ctx");
+  if (!c->mesh_ready || c->mesh_step != cycle)
+    return fail(c, "bgpu_mesh_source: bgpu_mesh_calculate_photon_energy has not run for cycle %u", cycle);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(c->ev[0], c->stream));
+  return source_from_device(c, cycle, c->mesh_dt, mesh_arr(c, MA_E_EMISSION), mesh_arr(c, MA_E_SOURCE),
+                            cycle == 1 ? mesh_arr(c, MA_E_CENSUS) : nullptr, total_E, n_new_out, n_total_out);
+}
+
+int bgpu_mesh_update_temperature(bgpu_ctx *c, bgpu_mesh_sums *sums) {
+  if (!c || !sums) return fail(c, "bgpu_mesh_update_temperature: null argument");
+  if (!c->mesh_ready) return fail(c, "bgpu_mesh_update_temperature: call bgpu_mesh_init first");
+  CU(c, cudaSetDevice(c->device));
+  const MeshPhysParams P = mesh_params(c);
+  ++c->launches;
+  // multi-rank: the all-reduced emission (src/mesh.h:343-345); one rank: m_emission_E itself
+  k_mesh_update_temperature<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(
+      P, c->mesh_redistributed ? P.E_emission_global : P.E_emission);
+  CU(c, cudaGetLastError());
+  return mesh_fetch_sums(c, (1u << MS_ABS) | (1u << MS_POST_MAT), sums);
+}
+
+int bgpu_mesh_get(bgpu_ctx *c, const char *name, double *out) {
+  if (!c || !name || !out) return fail(c, "bgpu_mesh_get: null argument");
+  if (!c->mesh_ready) return fail(c, "bgpu_mesh_get: call bgpu_mesh_init first");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t nc = c->mesh.n_cells;
+  const std::string k(name);
+  const double *src = nullptr;
+  if (k == "T_e") src = mesh_arr(c, MA_T_E);
+  else if (k == "T_r") src = mesh_arr(c, MA_T_R);
+  else if (k == "T_s") src = mesh_arr(c, MA_T_S);
+  else if (k == "f") src = c->d_f;
+  else if (k == "op_a") src = mesh_arr(c, MA_OP_A);
+  else if (k == "op_s") src = mesh_arr(c, MA_OP_S);
+  else if (k == "E_emission") src = mesh_arr(c, MA_E_EMISSION);
+  else if (k == "E_source") src = mesh_arr(c, MA_E_SOURCE);
+  else if (k == "E_census") src = mesh_arr(c, MA_E_CENSUS);
+  else if (k == "abs_E" || k == "track_E") {  // the (rank-summed) tallies of the last transport
+    if (ensure_pinned(c, 16 * nc)) return 1;
+    double *h = (double *)c->h_pinned;
+    CU(c, cudaMemcpyAsync(h, c->d_tally, 16 * nc, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const int o = k == "abs_E" ? 0 : 1;
+    for (uint64_t i = 0; i < nc; ++i) out[i] = h[2 * i + o];
+    return 0;
+  } else {
+    return fail(c, "bgpu_mesh_get: unknown array '%s'", name);
+  }
+  CU(c, cudaMemcpyAsync(out, src, 8 * nc, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 

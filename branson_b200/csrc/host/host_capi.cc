@@ -60,6 +60,7 @@ bhost_driver *bhost_create(const char *xml_path, int rank, int n_ranks, const bh
       Driver_Options o;
       o.tally_mode = opt->tally_mode;
       o.print = opt->print != 0;
+      o.mesh_on_device = opt->mesh_on_device != 0;
       d->driver = std::make_unique<Replicated_Driver>(*d->mesh, *d->state, *d->params, *d->comm, *d->gpu, o);
     }
   } catch (const std::exception &e) {
@@ -133,7 +134,15 @@ int bhost_get_array(const bhost_driver *d, const char *name, const double **data
   const std::string k(name);
   const std::vector<double> *v = nullptr;
   const Mesh &m = *d->mesh;
-  if (k == "T_e") v = &m.get_T_e();
+  if (d->driver && d->driver->mesh_on_device() &&
+      (k == "T_e" || k == "T_r" || k == "f" || k == "op_a" || k == "op_s" || k == "E_emission" || k == "E_source" ||
+       k == "E_census" || k == "abs_E" || k == "track_E")) {
+    try {
+      v = &d->driver->device_array(k);  // the cell state lives on the device: copy it over on request
+    } catch (const std::exception &) {
+      return 1;
+    }
+  } else if (k == "T_e") v = &m.get_T_e();
   else if (k == "T_r") v = &m.get_T_r();
   else if (k == "T_s") v = &m.get_T_s();
   else if (k == "f") v = &m.get_f();

@@ -262,6 +262,9 @@ public:
   const std::vector<double> &get_T_e() const { return T_e; }
   const std::vector<double> &get_T_r() const { return T_r; }
   const std::vector<double> &get_T_s() const { return T_s; }
+  const std::vector<Region> &get_regions() const { return regions; }
+  const std::vector<uint32_t> &get_region_index() const { return region_index; }
+  const std::vector<double> &get_T_r0() const { return T_r0; }
   double get_replicated_factor() const { return replicated_factor; }
   int get_rank() const { return rank; }
   int get_n_ranks() const { return n_ranks; }

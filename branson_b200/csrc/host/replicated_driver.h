@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdint>
 #include <iostream>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "comm.h"
@@ -37,6 +39,10 @@ struct Cycle_Report {
 struct Driver_Options {
   int tally_mode = BGPU_TALLY_ATOMIC;
   bool print = true;
+  // true: Mesh::calculate_photon_energy / update_temperature run on the device (bgpu_mesh_*): the cell state never
+  // leaves HBM and only the running sums cross PCIe.  false: the host Mesh (bit-identical to the reference's host code)
+  // with f / op_a / op_s / E arrays uploaded and the tallies downloaded every cycle.
+  bool mesh_on_device = false;
 };
 
 inline double wall_now() {
@@ -86,12 +92,123 @@ public:
   Replicated_Driver(Mesh &mesh_, IMC_State &imc_state_, const IMC_Parameters &imc_p_, const Comm &comm_,
                     GPU_Setup &gpu_setup_, const Driver_Options &opt_)
       : mesh(mesh_), imc_state(imc_state_), imc_p(imc_p_), comm(comm_), gpu_setup(gpu_setup_), opt(opt_),
-        abs_E(mesh_.get_n_global_cells(), 0.0), track_E(mesh_.get_n_global_cells(), 0.0) {}
+        abs_E(mesh_.get_n_global_cells(), 0.0), track_E(mesh_.get_n_global_cells(), 0.0) {
+    if (opt.mesh_on_device) {
+      // initialize_physical_properties (src/mesh.h:426-440) has run on the host Mesh; hand the static data over
+      std::vector<bgpu_region> regions;
+      for (const Region &r : mesh.get_regions())
+        regions.push_back(bgpu_region{r.get_opac_A(), r.get_opac_B(), r.get_opac_C(), r.get_opac_S(), r.get_cV(),
+                                      r.get_rho()});
+      gpu_setup.check(bgpu_mesh_init(gpu_setup.get_ctx(), (uint32_t)regions.size(), regions.data(),
+                                     mesh.get_region_index().data(), mesh.get_T_e().data(), mesh.get_T_r0().data(),
+                                     mesh.get_T_s().data()),
+                      "bgpu_mesh_init");
+    }
+  }
 
   bool finished() const { return imc_state.finished(); }
+  bool mesh_on_device() const { return opt.mesh_on_device; }
+
+  // device-mesh runs: a host copy of one per-cell array (T_e T_r f op_a op_s E_emission E_source E_census abs_E track_E)
+  const std::vector<double> &device_array(const std::string &name) {
+    std::vector<double> &v = dev_cache[name];
+    v.resize(mesh.get_n_global_cells());
+    gpu_setup.check(bgpu_mesh_get(gpu_setup.get_ctx(), name.c_str(), v.data()), "bgpu_mesh_get");
+    return v;
+  }
+
+  // one trip of the reference's while loop with the mesh physics on the device
+  Cycle_Report cycle_device_mesh() {
+    Cycle_Report rep{};
+    const int rank = comm.get_rank();
+    const double t_begin = wall_now();
+    rep.step = imc_state.get_step();
+    rep.dt = imc_state.get_dt();
+    rep.time = imc_state.get_time();
+    rep.next_dt = imc_state.get_next_dt();
+    if (rank == 0 && opt.print) imc_state.print_timestep_header();
+    bgpu_ctx *ctx = gpu_setup.get_ctx();
+
+    // mesh.calculate_photon_energy (src/replicated_driver.h:53)
+    bgpu_mesh_sums sums{};
+    gpu_setup.check(bgpu_mesh_calculate_photon_energy(ctx, imc_state.get_dt(), imc_state.get_step(), &sums),
+                    "bgpu_mesh_calculate_photon_energy");
+    if (!comm.single()) {
+      double global_source_E{sums.emission_E + sums.census_E + sums.source_E};  // src/mesh.h:291-294
+      comm.sum(&global_source_E, 1);
+      gpu_setup.check(bgpu_mesh_redistribute(ctx, global_source_E, &sums), "bgpu_mesh_redistribute");
+    }
+    imc_state.set_pre_mat_E(sums.pre_mat_E);
+    imc_state.set_emission_E(sums.emission_E);
+    imc_state.set_source_E(sums.source_E);
+    if (imc_state.get_step() == 1) imc_state.set_pre_census_E(sums.census_E);
+    double global_source_energy = sums.total_photon_E;
+    comm.sum(&global_source_energy, 1);
+    rep.global_source_energy = global_source_energy;
+    const double t1 = wall_now();
+    rep.t_calc_energy = t1 - t_begin;
+
+    uint64_t n_new = 0, n_total = 0;
+    gpu_setup.check(bgpu_mesh_source(ctx, imc_state.get_step(), global_source_energy, &n_new, &n_total),
+                    "bgpu_mesh_source");
+    bgpu_cycle_stats st{};
+    gpu_setup.check(bgpu_get_tallies(ctx, nullptr, nullptr, &st), "bgpu_get_tallies");
+    imc_state.set_pre_census_E(st.pre_census_E);
+    const double t3 = wall_now();
+    rep.t_source = t3 - t1;
+    if (rank == 0 && opt.print) std::cout << "source time: " << rep.t_source << std::endl;
+    imc_state.set_transported_particles(n_total);
+
+    comm.barrier();
+    const double t4 = wall_now();
+    gpu_setup.check(bgpu_transport(ctx, imc_state.get_next_dt(),
+                                   imc_p.get_transport_algorithm() == Constants::EVENT ? BGPU_EVENT : BGPU_HISTORY,
+                                   opt.tally_mode),
+                    "bgpu_transport");
+    const double t5 = wall_now();
+    rep.t_transport = t5 - t4;
+    if (!comm.single()) {
+      if (!comm.has_device_allreduce())
+        throw GPU_Error("mesh_on_device needs a device all-reduce (NCCL) for the tallies in multi-rank runs");
+      void *dptr = nullptr;
+      uint64_t n = 0;
+      gpu_setup.check(bgpu_tally_buffer(ctx, 0, &dptr, &n), "bgpu_tally_buffer");
+      comm.sum_device(dptr, n, bgpu_stream(ctx));
+    }
+    const double t6 = wall_now();
+    rep.t_allreduce = t6 - t5;
+    gpu_setup.check(bgpu_get_tallies(ctx, nullptr, nullptr, &rep.gpu), "bgpu_get_tallies");
+    imc_state.set_exit_E(rep.gpu.exit_E);
+    imc_state.set_post_census_E(rep.gpu.census_E);
+    imc_state.set_census_size(rep.gpu.n_census);
+    imc_state.set_rank_transport_runtime(rep.t_transport);
+
+    // mesh.update_temperature (src/replicated_driver.h:96)
+    gpu_setup.check(bgpu_mesh_update_temperature(ctx, &sums), "bgpu_mesh_update_temperature");
+    imc_state.set_absorbed_E(sums.absorbed_E);
+    imc_state.set_post_mat_E(sums.post_mat_E);
+    {
+      double rank_part = rep.gpu.census_E + rep.gpu.exit_E - rep.gpu.pre_census_E - st.new_photon_E;
+      comm.sum(&rank_part, 1);
+      rep.rad_balance_exact = sums.absorbed_E + rank_part;  // absorbed_E is a tree sum here (mesh_dev.cuh)
+    }
+    rep.t_update_T = wall_now() - t6;
+
+    comm.barrier();
+    if (rank) {  // for replicated, just let root do conservation (:100-104)
+      imc_state.set_absorbed_E(0.0);
+      imc_state.set_pre_mat_E(0.0);
+      imc_state.set_post_mat_E(0.0);
+    }
+    imc_state.print_conservation(comm, opt.print);
+    imc_state.next_time_step();
+    rep.t_cycle = wall_now() - t_begin;
+    return rep;
+  }
 
   // one trip of the reference's while loop (src/replicated_driver.h:47-121)
   Cycle_Report cycle() {
+    if (opt.mesh_on_device) return cycle_device_mesh();
     Cycle_Report rep{};
     const int rank = comm.get_rank();
     const double t_begin = wall_now();
@@ -176,6 +293,7 @@ private:
   GPU_Setup &gpu_setup;
   Driver_Options opt;
   std::vector<double> abs_E, track_E, last_abs_E, last_track_E;
+  std::map<std::string, std::vector<double>> dev_cache;
 };
 
 // the reference's entry point: run all cycles (src/replicated_driver.h:33-122)

@@ -58,6 +58,8 @@ EXPORTS = [
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
     "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
+    "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
+    "bgpu_mesh_update_temperature", "bgpu_mesh_get",
 ]
 
 

@@ -164,6 +164,38 @@ int bgpu_set_event_tail(bgpu_ctx *ctx, uint64_t n_active);
  * provably-equivalent closed form of the sequential walk; 0 = always walk the group array like the reference */
 int bgpu_set_group_walk(bgpu_ctx *ctx, int closed_form);
 
+/* ---- device-resident mesh physics (optional) ---------------------------------------------
+ * Mesh::calculate_photon_energy (src/mesh.h:237-323) and Mesh::update_temperature (src/mesh.h:327-362) on the device:
+ * T_e, T_r, opacities, Fleck factor, the emission / source / census energies and the tallies stay in HBM, only the
+ * running sums come back.  Replaces the per-cycle bgpu_set_cell_data + bgpu_source(host arrays) + bgpu_get_tallies
+ * sequence by
+ *   bgpu_mesh_calculate_photon_energy -> [n_ranks > 1: all-reduce the scalar, bgpu_mesh_redistribute] ->
+ *   bgpu_mesh_source -> bgpu_transport -> [all-reduce bgpu_tally_buffer] -> bgpu_mesh_update_temperature.
+ * Same expressions in the same operand order as the reference; pow() and the order of the running sums differ from the
+ * host path in the last bits (csrc/mesh_dev.cuh). */
+typedef struct {
+  double opac_A, opac_B, opac_C, opac_S, cV, rho; /* src/region.h */
+} bgpu_region;
+typedef struct {
+  double pre_mat_E, emission_E, census_E, source_E, total_photon_E; /* calculate_photon_energy / redistribute */
+  double absorbed_E, post_mat_E;                                    /* update_temperature */
+} bgpu_mesh_sums;
+/* static cell data: region table, region of every cell, initial T_e / T_r, source temperature T_s (0 without a
+ * SOURCE face) -- initialize_physical_properties, src/mesh.h:426-440 */
+int bgpu_mesh_init(bgpu_ctx *ctx, uint32_t n_regions, const bgpu_region *regions, const uint32_t *region_of_cell,
+                   const double *T_e, const double *T_r, const double *T_s);
+/* src/mesh.h:253-287: fills f / op_a / op_s (all groups) and this rank's E_emission / E_census / E_source */
+int bgpu_mesh_calculate_photon_energy(bgpu_ctx *ctx, double dt, uint32_t step, bgpu_mesh_sums *sums);
+/* src/mesh.h:291-315 (replicated runs with more than one rank): global_source_E is the all-reduced
+ * emission + census + source total of bgpu_mesh_calculate_photon_energy; the four energy sums are recomputed */
+int bgpu_mesh_redistribute(bgpu_ctx *ctx, double global_source_E, bgpu_mesh_sums *sums);
+/* bgpu_source from the device-resident energies of this cycle */
+int bgpu_mesh_source(bgpu_ctx *ctx, uint32_t cycle, double total_E, uint64_t *n_new, uint64_t *n_total);
+/* src/mesh.h:343-362 from the tally buffer (all-reduced by the caller in multi-rank runs) */
+int bgpu_mesh_update_temperature(bgpu_ctx *ctx, bgpu_mesh_sums *sums);
+/* copy one per-cell array to the host: T_e T_r T_s f op_a op_s E_emission E_source E_census abs_E track_E */
+int bgpu_mesh_get(bgpu_ctx *ctx, const char *name, double *out);
+
 /* known-answer hooks for the RNG unit tests (RNG(seed, stream) draws, src/RNG.h:262-285,318-330; raw Threefry2x64-20
  * of {ctr0, ctr1, key0, key1}, src/random123/threefry.h:196-282) */
 int bgpu_test_rng_draws(uint32_t seed, uint64_t stream, uint32_t n, double *out);

@@ -43,6 +43,7 @@ typedef struct {
   uint64_t photons_override;  /* 0: keep the deck's <photons> */
   double t_stop_override;     /* <=0: keep the deck's <t_stop> */
   int32_t force_replicated;   /* 1: treat dd_transport_type as REPLICATED (the multi-node deck says PARTICLE_PASS) */
+  int32_t mesh_on_device;     /* 1: calculate_photon_energy / update_temperature on the device (bgpu_mesh_*); 0: host Mesh */
 } bhost_options;
 
 typedef struct {

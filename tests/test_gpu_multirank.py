@@ -34,7 +34,9 @@ WORKER = textwrap.dedent("""
     path = os.path.join(os.environ["BRANSON_TMP"], f"deck_{rank}.xml")
     deck.write(path)
     comm = driver.TorchComm(f"cuda:{local}")
-    d = driver.Driver(path, n_groups=deck.n_groups, rank=rank, n_ranks=world, device=local, validate=True, comm=comm)
+    on_device = os.environ.get("BRANSON_MESH_ON_DEVICE") == "1"
+    d = driver.Driver(path, n_groups=deck.n_groups, rank=rank, n_ranks=world, device=local, validate=True, comm=comm,
+                      mesh_on_device=on_device)
     view = d.gpu_context()
     sim = port.OracleSim(deck, n_ranks=world)
     cyc = 0
@@ -70,13 +72,16 @@ def _free_port():
     return p
 
 
-def test_two_gpus_match_two_rank_oracle(tmp_path):
+@pytest.mark.parametrize("mesh", ["host", "device"])
+def test_two_gpus_match_two_rank_oracle(tmp_path, mesh):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 CUDA devices")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, BRANSON_ROOT=ROOT, BRANSON_TMP=str(tmp_path))
+    # mesh = device: calculate_photon_energy (with the rank redistribution) and update_temperature run on each GPU
+    env = dict(os.environ, BRANSON_ROOT=ROOT, BRANSON_TMP=str(tmp_path),
+               BRANSON_MESH_ON_DEVICE="1" if mesh == "device" else "0")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)], env=env,
                          capture_output=True, text=True, timeout=600)
