@@ -74,7 +74,7 @@ struct bgpu_ctx {
 
   // scratch (grown on demand)
   DevBuf scr_counts, scr_offsets, scr_tile_sum, scr_tile_off, scr_tiles, scr_ndep, scr_dep_off, scr_dep_cell,
-      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event;
+      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event, scr_tally_rep;
   void *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
 
@@ -82,6 +82,11 @@ struct bgpu_ctx {
   int block_threads = 128;
   int blocks_per_sm = 0;  // 0: occupancy query
   uint32_t chunk = 128;
+  bool chunk_auto = true;      // shrink the chunk when the work list is too short to give every warp several
+  uint32_t scatter_batch = 12;  // history kernel: parked scatters a warp waits for before sampling them together
+  int aggregate = 1;            // history kernel: combine same-cell deposits of a warp trip
+  int tally_copies = 0;         // replicated tallies of the history kernel (0: auto from the mesh size, 1: off)
+  uint32_t tally_copies_live = 0;  // copies the zeroed scr_tally_rep currently holds (+1 for the main tally)
   uint64_t event_tail = 0;   // active-list size below which BGPU_EVENT hands over to the history kernel (0: auto)
   uint32_t event_passes = 0;
 
@@ -441,6 +446,16 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   P.ctr_hi = c->ctr_hi;
   P.work_counter = c->d_work_counter;
   P.chunk = c->chunk;
+  if (c->chunk_auto) {
+    // at least ~8 chunks per resident warp, so the last chunks do not leave most of the machine idle (marshak /
+    // hot_zone: 1e6 photons over 2960 warps)
+    const uint64_t warps = (uint64_t)c->n_sm * 5 * 4;
+    uint64_t ch = c->n_work / (warps * 8);
+    ch = std::max<uint64_t>(32, std::min<uint64_t>(c->chunk, ch & ~31ull));
+    P.chunk = (uint32_t)ch;
+  }
+  P.scatter_batch = c->scatter_batch;
+  P.aggregate = c->aggregate;
   P.writeback_all = writeback_all ? 1 : 0;
   P.stats = c->d_stats;
   P.uniform_groups = (c->uniform_groups && c->closed_form_walk) ? 1 : 0;
@@ -464,7 +479,29 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   }
   if (tally_mode == BGPU_TALLY_ATOMIC) {
     CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
-    return launch_history<TM_ATOMIC>(c, P);
+    // replicated tallies: as many copies as fit 64 MB (L2-sized), at most 64; big meshes (8e6 cells) get none -- their
+    // deposits are spread over so many addresses that nothing serialises
+    uint32_t copies = c->tally_copies > 0 ? (uint32_t)c->tally_copies
+                                          : (uint32_t)std::min<uint64_t>(64, (64ull << 20) / (16ull * c->mesh.n_cells));
+    if (copies < 1) copies = 1;
+    if (copies > 1) {
+      const size_t bytes = 16ull * c->mesh.n_cells * (copies - 1);
+      if (c->tally_copies_live != copies) {
+        if (ensure(c, c->scr_tally_rep, bytes)) return 1;
+        CU(c, cudaMemsetAsync(c->scr_tally_rep.p, 0, bytes, c->stream));
+        c->tally_copies_live = copies;
+      }
+      P.tally_rep = (double2 *)c->scr_tally_rep.p;
+      P.tally_copies = copies;
+    }
+    if (launch_history<TM_ATOMIC>(c, P)) return 1;
+    if (copies > 1) {
+      ++c->launches;
+      k_fold_tally<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>((double2 *)c->d_tally, P.tally_rep,
+                                                                            c->mesh.n_cells, copies - 1);
+      CU(c, cudaGetLastError());
+    }
+    return 0;
   }
   // ---- deterministic: count deposits, scan, log, stable sort by cell, in-order segment sums ----
   const uint64_t n = c->n_work;
@@ -647,6 +684,11 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   cudaDeviceProp prop;
   CUC(cudaGetDeviceProperties(&prop, dev));
   c->n_sm = prop.multiProcessorCount;
+  // tuning sweeps (tools/): BGPU_SCATTER_BATCH, BGPU_AGGREGATE, BGPU_CHUNK override the defaults of a new context
+  if (const char *e = getenv("BGPU_SCATTER_BATCH")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->scatter_batch = (uint32_t)v; }
+  if (const char *e = getenv("BGPU_AGGREGATE")) c->aggregate = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("BGPU_TALLY_COPIES")) { const int v = atoi(e); if (v >= 0 && v <= 1024) c->tally_copies = v; }
+  if (const char *e = getenv("BGPU_CHUNK")) { const int v = atoi(e); if (v > 0) { c->chunk = (uint32_t)v; c->chunk_auto = false; } }
   CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CUC(cudaEventCreate(&ev));
   c->mesh.nx = d->nx; c->mesh.ny = d->ny; c->mesh.nz = d->nz; c->mesh.G = d->n_groups;
@@ -694,7 +736,7 @@ void bgpu_destroy(bgpu_ctx *c) {
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->scr_counts, &c->scr_offsets, &c->scr_tile_sum, &c->scr_tile_off, &c->scr_tiles, &c->scr_ndep,
                     &c->scr_dep_off, &c->scr_dep_cell, &c->scr_dep_val, &c->scr_sort, &c->scr_keys_out,
-                    &c->scr_vals_in, &c->scr_vals_out, &c->scr_seg, &c->scr_aos, &c->scr_event};
+                    &c->scr_vals_in, &c->scr_vals_out, &c->scr_seg, &c->scr_aos, &c->scr_event, &c->scr_tally_rep};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
@@ -1141,7 +1183,22 @@ int bgpu_set_launch(bgpu_ctx *c, int block_threads, int blocks_per_sm, int chunk
     c->block_threads = block_threads;
   }
   c->blocks_per_sm = blocks_per_sm;
-  if (chunk > 0) c->chunk = (uint32_t)chunk;
+  if (chunk > 0) { c->chunk = (uint32_t)chunk; c->chunk_auto = false; }
+  return 0;
+}
+
+int bgpu_set_divergence(bgpu_ctx *c, int scatter_batch, int aggregate_deposits) {
+  if (!c) return 1;
+  if (scatter_batch > 32) return fail(c, "bgpu_set_divergence: scatter_batch is a lane count (1..32, 0 = keep)");
+  if (scatter_batch > 0) c->scatter_batch = (uint32_t)scatter_batch;
+  if (aggregate_deposits >= 0) c->aggregate = aggregate_deposits ? 1 : 0;
+  return 0;
+}
+
+int bgpu_set_tally_copies(bgpu_ctx *c, int copies) {
+  if (!c) return 1;
+  if (copies < 0 || copies > 1024) return fail(c, "bgpu_set_tally_copies: 0 (auto), 1 (off) .. 1024");
+  c->tally_copies = copies;
   return 0;
 }
 

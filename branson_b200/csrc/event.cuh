@@ -70,9 +70,12 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
   C.uniform_groups = P.uniform_groups != 0;
   const unsigned lane_id = threadIdx.x & 31u;
 
-  auto deposit = [&](uint32_t cell, double a, double t) {
-    atomicAdd(&P.tally[cell].x, a);
-    atomicAdd(&P.tally[cell].y, t);
+  const uint32_t bcpack = pack_bc(P.mesh.bc);
+  auto deposit = [&](bool dep, uint32_t cell, double a, double t, unsigned) {
+    if (dep) {
+      atomicAdd(&P.tally[cell].x, a);
+      atomicAdd(&P.tally[cell].y, t);
+    }
   };
 
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
       int r = R_CONTINUE;
 #pragma unroll 1
       for (int step = 0; step < EV_MAX_ADVANCE && r == R_CONTINUE; ++step)
-        r = advance_event(S, C, P.mesh.bc, deposit, descriptor);
+        r = advance_event(S, C, bcpack, deposit, descriptor, 0u);
       if (r == R_DONE) {
         close_visit(S);
         stats_add(s_stats, S);

@@ -62,6 +62,14 @@ struct TransportParams {
   const uint32_t *carry_lk;
   int uniform_groups;  // every cell's abs_groups are all equal (gray decks, Cell::set_op_a): closed-form group walk
   int resume_pending_scatter;  // the photons of index_list are parked AT a scatter (else after a non-scatter event)
+  // divergence / contention control of the history kernel (bgpu_set_tuning; results do not depend on either)
+  uint32_t scatter_batch;  // a warp samples its parked scatters once this many lanes wait at one (1 = immediately)
+  int aggregate;           // combine the same-cell deposits of a warp trip into one pair of atomics
+  // Replicated tallies: warp w deposits into copy w % tally_copies (copy 0 = `tally`, copies 1.. = `tally_rep`, n_cells
+  // entries each, zero at launch); k_fold_tally adds the copies into `tally` afterwards.  Same-address FP64 reductions
+  // serialise in L2, so a few hot cells (hot_zone's corner, marshak's 25 cells) otherwise throttle the whole grid.
+  double2 *tally_rep;
+  uint32_t tally_copies;
 };
 
 // Photon state of one lane, kept in registers for the whole history.
@@ -142,12 +150,26 @@ __device__ __forceinline__ void close_visit(PState &S) {
   S.gmask = 0;
 }
 
+// The six domain boundary conditions packed three bits each (bc_type values 0..4), indexed by face: a register
+// instead of a divergent constant-bank lookup.
+__host__ __device__ __forceinline__ uint32_t pack_bc(const int *bc) {
+  uint32_t p = 0;
+  for (int s = 0; s < 6; ++s) p |= ((uint32_t)bc[s] & 7u) << (3 * s);
+  return p;
+}
+
 // One trip of the reference's while(active) loop (src/history_based_transport.h:55-139) up to the event dispatch.
 // Returns R_SCATTER with the scatter not yet sampled (the caller runs scatter_event), R_DONE with `descriptor` set, or
-// R_CONTINUE after a cell crossing / reflection.  `bc` are the six domain boundary conditions.
+// R_CONTINUE after a cell crossing / reflection.  `bcpack` = pack_bc(domain boundary conditions).
+//
+// Divergence control: the boundary branch is straight-line code (axis / direction / boundary type resolved with
+// selects), so lanes crossing different faces run it together -- ncu showed the branchy form executing the crossing
+// path six times per trip at 4 of 32 lanes -- and every deposit of the trip (cell left, photon killed / escaped /
+// reaching census) is issued from ONE converged site: deposit(do_it, cell, abs, trk, lanes), called by every lane of
+// `lanes` (the lanes that entered this function together), which lets the caller combine same-cell deposits.
 template <class Deposit>
-__device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int *bc, Deposit &&deposit,
-                                             uint8_t &descriptor) {
+__device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uint32_t bcpack, Deposit &&deposit,
+                                             uint8_t &descriptor, const unsigned lanes) {
   const double total_sigma_s = (1.0 - S.f) * S.sig_a + S.sig_s;
   double d_scat = 1.0e100;
   if (total_sigma_s > 0.0) {
@@ -189,58 +211,60 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const int
   S.z += S.az * d;
   S.life -= d;
 
+  int r = R_CONTINUE;
+  bool dep = false, crossed = false;
+  const uint32_t dep_cell = S.cell;
   if (S.E / S.E0 < K_CUTOFF) {  // energy cutoff first (:85-91)
     S.loc_abs += S.E;
-    deposit(S.cell, S.loc_abs, S.loc_trk);
+    dep = true;
     descriptor = EV_KILLED;
-    return R_DONE;
-  }
-  if (d == d_scat) return R_SCATTER;
-  if (d == d_bnd) {
+    r = R_DONE;
+  } else if (d == d_scat) {  // (:94-101), sampled by the caller
+    r = R_SCATTER;
+  } else if (d == d_bnd) {  // (:103-131)
     const uint32_t axis = S.surface >> 1;
-    const bool pos_dir = S.surface & 1u;
-    bool domain_face;
-    if (axis == 0) domain_face = pos_dir ? (S.i == (int)C.nx - 1) : (S.i == 0);
-    else if (axis == 1) domain_face = pos_dir ? (S.j == (int)C.ny - 1) : (S.j == 0);
-    else domain_face = pos_dir ? (S.k == (int)C.nz - 1) : (S.k == 0);
-    const int bcv = domain_face ? bc[S.surface] : BC_ELEMENT;
-    if (bcv == BC_ELEMENT) {  // (:104-114)
-      deposit(S.cell, S.loc_abs, S.loc_trk);
-      close_visit(S);
-      const int step = pos_dir ? 1 : -1;
-      if (axis == 0) { S.i += step; S.cell += (uint32_t)step; }
-      else if (axis == 1) { S.j += step; S.cell += (uint32_t)(step * (int)C.nx); }
-      else { S.k += step; S.cell += (uint32_t)(step * (int)C.sxy); }
-      S.loc_abs = 0.0;
-      S.loc_trk = 0.0;
-      ++S.c_cr;
-      enter_cell(S, C);
-      return R_CONTINUE;
-    }
-    if (bcv == BC_VACUUM || bcv == BC_SOURCE) {  // (:122-126)
-      deposit(S.cell, S.loc_abs, S.loc_trk);
-      descriptor = EV_EXIT;
-      return R_DONE;
-    }
-    if (bcv == BC_PROCESSOR) {
-      // never produced in replicated mode (every rank owns the whole mesh); kept for fidelity (:115-121)
-      deposit(S.cell, S.loc_abs, S.loc_trk);
-      descriptor = EV_PASS;
-      return R_DONE;
-    }
-    // REFLECT (:127-130)
-    if (axis == 0) S.ax = -S.ax;
-    else if (axis == 1) S.ay = -S.ay;
-    else S.az = -S.az;
-    ++S.c_rf;
-    return R_CONTINUE;
-  }
-  if (d == d_cen) {  // (:133-138)
-    deposit(S.cell, S.loc_abs, S.loc_trk);
+    const bool pos_dir = (S.surface & 1u) != 0u;
+    const int pos = (axis == 0u) ? S.i : ((axis == 1u) ? S.j : S.k);
+    const int lim = (int)((axis == 0u) ? C.nx : ((axis == 1u) ? C.ny : C.nz)) - 1;
+    const bool domain_face = pos == (pos_dir ? lim : 0);
+    const uint32_t bcv = domain_face ? ((bcpack >> (3u * S.surface)) & 7u) : (uint32_t)BC_ELEMENT;
+    const bool cross = bcv == (uint32_t)BC_ELEMENT;   // (:104-114)
+    const bool reflect = bcv == (uint32_t)BC_REFLECT;  // (:127-130)
+    // ELEMENT: step into the neighbour (cell = i + nx (j + ny k)); every other boundary type leaves i, j, k alone
+    const int step = cross ? (pos_dir ? 1 : -1) : 0;
+    S.i += (axis == 0u) ? step : 0;
+    S.j += (axis == 1u) ? step : 0;
+    S.k += (axis == 2u) ? step : 0;
+    S.cell += (uint32_t)(step * (int)((axis == 0u) ? 1u : ((axis == 1u) ? C.nx : C.sxy)));
+    S.c_cr += cross ? 1u : 0u;
+    // REFLECT: flip the direction component normal to the face
+    S.ax = (reflect && axis == 0u) ? -S.ax : S.ax;
+    S.ay = (reflect && axis == 1u) ? -S.ay : S.ay;
+    S.az = (reflect && axis == 2u) ? -S.az : S.az;
+    S.c_rf += reflect ? 1u : 0u;
+    // VACUUM or SOURCE: the photon escapes (:122-126); PROCESSOR (never produced in replicated mode, every rank owns
+    // the whole mesh; kept for fidelity, :115-121): it would be passed on
+    const bool leave = !cross && !reflect;
+    descriptor = leave ? ((bcv == (uint32_t)BC_PROCESSOR) ? EV_PASS : EV_EXIT) : descriptor;
+    r = leave ? R_DONE : R_CONTINUE;
+    dep = !reflect;
+    crossed = cross;
+  } else if (d == d_cen) {  // (:133-138)
+    dep = true;
     descriptor = EV_CENSUS;
-    return R_DONE;
+    r = R_DONE;
   }
-  return R_CONTINUE;  // only reachable through NaN distances (the reference loops as well)
+  // (no branch taken: only reachable through NaN distances -- the reference loops as well)
+  if (crossed) {  // the loads of the new cell are in flight before the tally traffic of the old one is issued
+    close_visit(S);
+    enter_cell(S, C);
+  }
+  deposit(dep, dep_cell, S.loc_abs, S.loc_trk, lanes);
+  if (dep) {
+    S.loc_abs = 0.0;
+    S.loc_trk = 0.0;
+  }
+  return r;
 }
 
 // The scatter event (:94-101).  Its draws use consecutive counters, so they are evaluated as four interleaved
@@ -383,13 +407,50 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   uint32_t ndep = 0;
   uint64_t dep_pos = 0;
 
-  auto deposit = [&](uint32_t cell, double a, double t) {
+  const uint32_t bcpack = pack_bc(P.mesh.bc);
+  double2 *my_tally = P.tally;
+  if (MODE == TM_ATOMIC && P.tally_copies > 1u) {
+    const uint32_t copy = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % P.tally_copies;
+    if (copy) my_tally = P.tally_rep + (size_t)(copy - 1u) * P.mesh.n_cells;
+  }
+  const uint32_t scatter_batch = P.scatter_batch;
+  const bool aggregate = P.aggregate != 0;
+
+  // Called by every lane of `lanes` together; `dep` says whether this lane has a deposit.
+  auto deposit = [&](bool dep, uint32_t cell, double a, double t, unsigned lanes) {
     if (MODE == TM_ATOMIC) {
-      atomicAdd(&P.tally[cell].x, a);
-      atomicAdd(&P.tally[cell].y, t);
+      if (aggregate) {
+        // Warp-aggregated tallies: lanes depositing into the same cell are combined by a segmented tree reduction over
+        // their peer set and the group's first lane issues the one pair of atomics.  Pays off where many photons sit
+        // in few cells (marshak: 25 cells; hot_zone: a 5 x 5 hot corner), where same-address reductions serialise in L2.
+        const unsigned dm = __ballot_sync(lanes, dep);
+        if (dep) {
+          const unsigned peers = __match_any_sync(dm, cell);
+          const unsigned below = peers & lt_mask;
+          if (__any_sync(dm, (peers & (peers - 1u)) != 0u)) {
+            unsigned rel = __popc(below);                       // rank inside the group
+            unsigned higher = peers & ~(lt_mask | (1u << lane_id));
+            while (__any_sync(dm, higher != 0u)) {
+              const int next = __ffs(higher);                   // nearest remaining peer above this lane (1-based)
+              const int src = next ? next - 1 : (int)lane_id;
+              const double ra = __shfl_sync(dm, a, src), rt = __shfl_sync(dm, t, src);
+              if (next) { a += ra; t += rt; }
+              higher &= ~__ballot_sync(dm, (rel & 1u) != 0u);   // odd ranks have been absorbed by their left peer
+              rel >>= 1;
+            }
+          }
+          if (below == 0u) {
+            atomicAdd(&my_tally[cell].x, a);
+            atomicAdd(&my_tally[cell].y, t);
+          }
+        }
+      } else if (dep) {
+        atomicAdd(&my_tally[cell].x, a);
+        atomicAdd(&my_tally[cell].y, t);
+      }
     } else if (MODE == TM_COUNT) {
-      ++ndep;
-    } else {
+      if (dep) ++ndep;
+    } else if (dep) {
       P.dep_cell[dep_pos] = cell;
       P.dep_val[dep_pos] = make_double2(a, t);
       ++dep_pos;
@@ -427,7 +488,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
             S.loc_abs = acc.x; S.loc_trk = acc.y;
             S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
             S.c_lk = P.carry_lk[idx];
-            pending_scatter = P.resume_pending_scatter != 0;
+            pending_scatter = P.resume_pending_scatter != 0;  // (pstate_load has fetched this visit's f, sigma_a, sigma_s)
           }
           ndep = 0;
           if (MODE == TM_LOG) dep_pos = P.dep_off[idx];
@@ -439,37 +500,69 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
         break;  // nothing left to fetch and nobody is working
       }
     }
-    if (!active) continue;
 
-    // ---------------- one event ----------------
-    if (RESUME && pending_scatter) {
-      scatter_event(S, C);  // the parked scatter (pstate_load has fetched this visit's f, sigma_a, sigma_s)
-      pending_scatter = false;
-    }
-    uint8_t descriptor = EV_PASS;
-    const int r = advance_event(S, C, P.mesh.bc, deposit, descriptor);
-    if (r == R_SCATTER) {
-      scatter_event(S, C);
-    } else if (r == R_DONE) {
-      close_visit(S);
-      if (MODE != TM_COUNT) stats_add(s_stats, S);
-      const uint32_t idx = my_idx;
-      if (MODE == TM_COUNT) {
-        P.ndep[idx] = ndep;
-      } else {
-        P.desc[idx] = descriptor;
-        P.ph.ee[idx] = make_double2(S.E, S.E0);
-        if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
-        if (COUNTERS)
-          reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(events_of_finished(S), S.c_sc, S.c_cr, S.c_rf);
+    // ---------------- one event for every lane that is not parked at a scatter ----------------
+    const bool go = active && !pending_scatter;
+    const unsigned adv = __ballot_sync(FULL, go);
+    if (go) {
+      uint8_t descriptor = EV_PASS;
+      const int r = advance_event(S, C, bcpack, deposit, descriptor, adv);
+      if (r == R_SCATTER) {
+        pending_scatter = true;
+      } else if (r == R_DONE) {
+        close_visit(S);
+        if (MODE != TM_COUNT) stats_add(s_stats, S);
+        const uint32_t idx = my_idx;
+        if (MODE == TM_COUNT) {
+          P.ndep[idx] = ndep;
+        } else {
+          P.desc[idx] = descriptor;
+          P.ph.ee[idx] = make_double2(S.E, S.E0);
+          if (P.writeback_all || descriptor == EV_CENSUS) pstate_store_full(S, P.ph, idx);
+          if (COUNTERS)
+            reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(events_of_finished(S), S.c_sc, S.c_cr, S.c_rf);
+        }
+        active = false;
       }
-      active = false;
+    }
+
+    // ---------------- scatters, sampled by the warp's parked lanes together ----------------
+    // The scatter is the expensive event (4 of its 5 Threefry evaluations, sincos, sqrt).  A lane that reaches one
+    // parks; the warp samples the parked scatters once `scatter_batch` lanes wait, or when no lane is left that could
+    // advance instead.  In scattering-dominated cycles nearly every lane parks on every trip and this is the old
+    // one-event-per-trip loop; in mixed cycles (big_cube: 1 event in 6 is a scatter) the scatter code runs at
+    // >= scatter_batch lanes instead of ~5.  Per-photon results cannot change: a history depends on nothing but its own
+    // state.
+    const unsigned parked = __ballot_sync(FULL, pending_scatter);
+    if (parked) {
+      const unsigned movable = __ballot_sync(FULL, active && !pending_scatter);
+      if ((uint32_t)__popc(parked) >= scatter_batch || movable == 0u) {
+        if (pending_scatter) {
+          scatter_event(S, C);
+          pending_scatter = false;
+        }
+      }
     }
   }
 
   // ---------------- statistics: one global atomic per CTA and counter ----------------
   __syncthreads();
   if (MODE != TM_COUNT) stats_flush(s_stats, P.stats);
+}
+
+// tally[i] += rep[0][i] + rep[1][i] + ... in copy order (a fixed order: the fold adds no run-to-run noise of its own),
+// and the copies are zeroed for the next launch.
+__global__ void k_fold_tally(double2 *tally, double2 *rep, uint32_t n_cells, uint32_t n_rep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  double2 acc = tally[i];
+  for (uint32_t r = 0; r < n_rep; ++r) {
+    const double2 v = rep[(size_t)r * n_cells + i];
+    acc.x += v.x;
+    acc.y += v.y;
+    rep[(size_t)r * n_cells + i] = make_double2(0.0, 0.0);
+  }
+  tally[i] = acc;
 }
 
 }  // namespace bg

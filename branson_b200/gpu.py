@@ -57,7 +57,7 @@ EXPORTS = [
     "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
-    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_divergence", "bgpu_set_tally_copies", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
     "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
     "bgpu_mesh_update_temperature", "bgpu_mesh_get",
 ]
@@ -94,6 +94,8 @@ def lib():
         L.bgpu_list_size.restype = u64
         L.bgpu_enable_counters.argtypes = [vp, i32]
         L.bgpu_set_launch.argtypes = [vp, i32, i32, i32]
+        L.bgpu_set_divergence.argtypes = [vp, i32, i32]
+        L.bgpu_set_tally_copies.argtypes = [vp, i32]
         L.bgpu_set_event_tail.argtypes = [vp, u64]
         L.bgpu_set_group_walk.argtypes = [vp, i32]
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
@@ -210,6 +212,12 @@ class Context:
 
     def set_launch(self, block_threads=0, blocks_per_sm=0, chunk=0):
         self._ck(lib().bgpu_set_launch(self._h, block_threads, blocks_per_sm, chunk))
+
+    def set_divergence(self, scatter_batch=0, aggregate=-1):
+        self._ck(lib().bgpu_set_divergence(self._h, scatter_batch, aggregate))
+
+    def set_tally_copies(self, copies=0):
+        self._ck(lib().bgpu_set_tally_copies(self._h, copies))
 
     def set_event_tail(self, n_active):
         self._ck(lib().bgpu_set_event_tail(self._h, n_active))

@@ -23,6 +23,11 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
     "smsp__inst_executed_op_global_red.sum", "smsp__sass_inst_executed_op_local_ld.sum",
     "smsp__sass_inst_executed_op_local_st.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_op_read_hit_rate.pct", "lts__t_sector_op_red_hit_rate.pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "lts__average_t_sector_hit_rate_realtime.pct",
 ]
 lines = [f"# ncu --set full summary of `{rep}`", ""]
 traffic = []
