@@ -432,6 +432,23 @@ int run_event(bgpu_ctx *c, TransportParams P) {
   return 0;
 }
 
+// Replicated tallies (transport.cuh, TransportParams::tally_rep): as many copies as fit 64 MB (L2-sized), at most 64;
+// big meshes (8e6 cells) get none -- their deposits are spread over so many addresses that nothing serialises.  The
+// copies are zero between launches (k_fold_tally re-zeroes them).
+int prepare_tally_copies(bgpu_ctx *c) {
+  uint32_t copies = c->tally_copies > 0 ? (uint32_t)c->tally_copies
+                                        : (uint32_t)std::min<uint64_t>(64, (64ull << 20) / (16ull * c->mesh.n_cells));
+  if (copies < 1) copies = 1;
+  if (c->tally_copies_live == copies) return 0;
+  if (copies > 1) {
+    const size_t bytes = 16ull * c->mesh.n_cells * (copies - 1);
+    if (ensure(c, c->scr_tally_rep, bytes)) return 1;
+    CU(c, cudaMemsetAsync(c->scr_tally_rep.p, 0, bytes, c->stream));
+  }
+  c->tally_copies_live = copies;
+  return 0;
+}
+
 TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   TransportParams P{};
   P.ph = c->work;
@@ -454,6 +471,8 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
     ch = std::max<uint64_t>(32, std::min<uint64_t>(c->chunk, ch & ~31ull));
     P.chunk = (uint32_t)ch;
   }
+  P.inv_sxy = 1.0 / ((double)c->mesh.nx * (double)c->mesh.ny);
+  P.inv_nx = 1.0 / (double)c->mesh.nx;
   P.scatter_batch = c->scatter_batch;
   P.aggregate = c->aggregate;
   P.writeback_all = writeback_all ? 1 : 0;
@@ -479,18 +498,9 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   }
   if (tally_mode == BGPU_TALLY_ATOMIC) {
     CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
-    // replicated tallies: as many copies as fit 64 MB (L2-sized), at most 64; big meshes (8e6 cells) get none -- their
-    // deposits are spread over so many addresses that nothing serialises
-    uint32_t copies = c->tally_copies > 0 ? (uint32_t)c->tally_copies
-                                          : (uint32_t)std::min<uint64_t>(64, (64ull << 20) / (16ull * c->mesh.n_cells));
-    if (copies < 1) copies = 1;
+    if (prepare_tally_copies(c)) return 1;
+    const uint32_t copies = c->tally_copies_live;
     if (copies > 1) {
-      const size_t bytes = 16ull * c->mesh.n_cells * (copies - 1);
-      if (c->tally_copies_live != copies) {
-        if (ensure(c, c->scr_tally_rep, bytes)) return 1;
-        CU(c, cudaMemsetAsync(c->scr_tally_rep.p, 0, bytes, c->stream));
-        c->tally_copies_live = copies;
-      }
       P.tally_rep = (double2 *)c->scr_tally_rep.p;
       P.tally_copies = copies;
     }
@@ -726,6 +736,11 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
     return 1;
   }
 #undef CUC
+  if (prepare_tally_copies(c)) {  // allocated here so that no cycle's timing carries a cudaMalloc
+    g_create_error = c->err;
+    bgpu_destroy(c);
+    return 1;
+  }
   *out = c;
   return 0;
 }

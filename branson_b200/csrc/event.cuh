@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
   C.f = P.f; C.opa = P.opa; C.ops = P.ops;
   C.ctr_hi = P.ctr_hi;
   C.uniform_groups = P.uniform_groups != 0;
+  C.inv_sxy = P.inv_sxy; C.inv_nx = P.inv_nx;
   const unsigned lane_id = threadIdx.x & 31u;
 
   const uint32_t bcpack = pack_bc(P.mesh.bc);

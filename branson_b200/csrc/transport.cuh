@@ -56,6 +56,7 @@ struct TransportParams {
   double2 *dep_val;
   unsigned long long *stats;
   // RESUME launches (the tail of the event-based variant, event.cuh)
+  double inv_sxy, inv_nx;   // 1 / (nx ny), 1 / nx: cell -> (i, j, k) without integer division (set by make_params)
   const uint32_t *index_list;
   const double2 *carry_acc;
   const uint4 *carry_cnt;
@@ -92,7 +93,18 @@ struct PCtx {
   const double *f, *opa, *ops;
   uint64_t ctr_hi;
   bool uniform_groups;
+  double inv_sxy, inv_nx;
 };
+
+// n / d for n < 2^32 through the double reciprocal inv = fl(1 / d): the product is within 2^-20 / d of the true
+// quotient, closer than any non-integer quotient is to an integer, so truncation can only be off (by -1) when d divides
+// n exactly -- one fix-up.  (The SASS of an integer division is ~20 instructions at 1-2 active lanes per refill.)
+__device__ __forceinline__ uint32_t div_by_inv(uint32_t n, uint32_t d, double inv, uint32_t &rem) {
+  uint32_t q = __double2uint_rz(__uint2double_rn(n) * inv);
+  rem = n - q * d;
+  if (rem >= d) { ++q; rem -= d; }
+  return q;
+}
 
 enum : int { R_CONTINUE = 0, R_DONE = 1, R_SCATTER = 2 };
 
@@ -125,10 +137,10 @@ __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint
   S.stream = sg.x;
   S.cell = (uint32_t)sg.y;
   S.group = (uint32_t)(sg.y >> 32);
-  const uint32_t kk = S.cell / C.sxy;
-  const uint32_t rem = S.cell - kk * C.sxy;
-  const uint32_t jj = rem / C.nx;
-  S.k = (int)kk; S.j = (int)jj; S.i = (int)(rem - jj * C.nx);
+  uint32_t rem, ii;
+  const uint32_t kk = div_by_inv(S.cell, C.sxy, C.inv_sxy, rem);
+  const uint32_t jj = div_by_inv(rem, C.nx, C.inv_nx, ii);
+  S.k = (int)kk; S.j = (int)jj; S.i = (int)ii;
   S.loc_abs = 0.0; S.loc_trk = 0.0;
   S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
@@ -330,7 +342,8 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
   }
   if ((uint32_t)g != S.group) {
     S.group = (uint32_t)g;
-    load_xs(S, C);
+    if (C.uniform_groups) S.gmask |= 1u << (S.group & 31u);  // same opacities in every group of the cell: nothing to
+    else load_xs(S, C);                                        // fetch (the lookup is still counted, section 8d)
   }
 }
 
@@ -339,6 +352,35 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
 __device__ __forceinline__ void stat_add32(uint32_t *s_stats, int which, uint32_t v) {
   const uint32_t old = atomicAdd(&s_stats[2 * which], v);
   if (old + v < old) atomicAdd(&s_stats[2 * which + 1], 1u);
+}
+// Running totals of the histories a lane has finished, kept in registers (the per-history update is five integer adds
+// at the 1-2 lanes that retire per trip, where shared-memory atomics cost 12 instructions and a short-scoreboard wait)
+// and flushed to the CTA's shared counters at the end of the kernel, or early if a 32-bit total is about to wrap.
+struct LaneStats {
+  uint32_t n, sc, cr, rf, lk;
+};
+__device__ __forceinline__ void lane_stats_flush(uint32_t *s_stats, LaneStats &L) {
+  stat_add32(s_stats, ST_SCATTERS, L.sc);
+  stat_add32(s_stats, ST_CROSSINGS, L.cr);
+  stat_add32(s_stats, ST_REFLECTIONS, L.rf);
+  stat_add32(s_stats, ST_LOOKUPS, L.lk);
+  stat_add32(s_stats, ST_DEPOSITS, L.n);   // + crossings: added by stats_flush (one deposit per cell left + the last)
+  stat_add32(s_stats, ST_EVENTS, L.n);     // + scatters + crossings + reflections: likewise (events_of_finished)
+  L.n = L.sc = L.cr = L.rf = L.lk = 0u;
+}
+__device__ __forceinline__ void lane_stats_add(uint32_t *s_stats, LaneStats &L, const PState &S) {
+  L.n += 1u; L.sc += S.c_sc; L.cr += S.c_cr; L.rf += S.c_rf; L.lk += S.c_lk;
+  if ((L.sc | L.cr | L.rf | L.lk) & 0x80000000u) lane_stats_flush(s_stats, L);
+}
+// stats_flush for kernels that used LaneStats: ST_EVENTS / ST_DEPOSITS hold only the history count so far
+__device__ __forceinline__ void stats_flush_derived(const uint32_t *s_stats, unsigned long long *g_stats) {
+  if (threadIdx.x < 6) {
+    auto val = [&](int w) { return ((unsigned long long)s_stats[2 * w + 1] << 32) | s_stats[2 * w]; };
+    unsigned long long v = val((int)threadIdx.x);
+    if (threadIdx.x == ST_EVENTS) v += val(ST_SCATTERS) + val(ST_CROSSINGS) + val(ST_REFLECTIONS);
+    if (threadIdx.x == ST_DEPOSITS) v += val(ST_CROSSINGS);
+    if (v) atomicAdd(&g_stats[threadIdx.x], v);
+  }
 }
 __device__ __forceinline__ void stats_add(uint32_t *s_stats, const PState &S) {
   stat_add32(s_stats, ST_EVENTS, events_of_finished(S));
@@ -356,7 +398,7 @@ __device__ __forceinline__ void stats_flush(const uint32_t *s_stats, unsigned lo
 }
 
 #ifndef BG_MIN_BLOCKS
-#define BG_MIN_BLOCKS 4
+#define BG_MIN_BLOCKS 5
 #endif
 
 // RESUME: the launch continues histories that the event-based passes (event.cuh) parked at a pending scatter: photon
@@ -383,6 +425,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   C.f = P.f; C.opa = P.opa; C.ops = P.ops;
   C.ctr_hi = P.ctr_hi;
   C.uniform_groups = P.uniform_groups != 0;
+  C.inv_sxy = P.inv_sxy; C.inv_nx = P.inv_nx;
   const unsigned FULL = 0xffffffffu;
   const unsigned lane_id = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane_id) - 1u;
@@ -403,6 +446,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
   S.p_grp = 0.0;
+  LaneStats LS{0u, 0u, 0u, 0u, 0u};
   uint32_t my_idx = 0;
   uint32_t ndep = 0;
   uint64_t dep_pos = 0;
@@ -511,7 +555,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
         pending_scatter = true;
       } else if (r == R_DONE) {
         close_visit(S);
-        if (MODE != TM_COUNT) stats_add(s_stats, S);
+        if (MODE != TM_COUNT) lane_stats_add(s_stats, LS, S);
         const uint32_t idx = my_idx;
         if (MODE == TM_COUNT) {
           P.ndep[idx] = ndep;
@@ -546,8 +590,9 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   }
 
   // ---------------- statistics: one global atomic per CTA and counter ----------------
+  if (MODE != TM_COUNT) lane_stats_flush(s_stats, LS);
   __syncthreads();
-  if (MODE != TM_COUNT) stats_flush(s_stats, P.stats);
+  if (MODE != TM_COUNT) stats_flush_derived(s_stats, P.stats);
 }
 
 // tally[i] += rep[0][i] + rep[1][i] + ... in copy order (a fixed order: the fold adds no run-to-run noise of its own),

@@ -33,7 +33,7 @@ def _close(got, want, scale=None, what=""):
 
 
 def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATOMIC, max_cycles=None, launch=None,
-                event_tail=None, closed_form_walk=True, group_arrays=False):
+                event_tail=None, closed_form_walk=True, group_arrays=False, tuning=None):
     sim = port.OracleSim(deck, n_ranks=n_ranks)
     ctxs = None
     cyc = 0
@@ -51,6 +51,9 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
                 if event_tail is not None:
                     c.set_event_tail(event_tail)
                 c.set_group_walk(closed_form_walk)
+                if tuning:
+                    c.set_divergence(tuning.get("scatter_batch", 0), tuning.get("aggregate", -1))
+                    c.set_tally_copies(tuning.get("tally_copies", 0))
         dt, next_dt, gse = sim.get("dt")[0], sim.get("next_dt")[0], sim.get("global_source_energy")[0]
         f, op_a, op_s = sim.get("f"), sim.get("op_a"), sim.get("op_s")
         tot_abs = np.zeros(deck.n_cells)
@@ -205,6 +208,20 @@ def test_deterministic_mode_is_bitwise_reproducible():
 def test_small_chunks_and_few_blocks_give_identical_photons():
     # work distribution must not change any per-photon result (SURVEY 8a note N5)
     _run_cycles(decks.hot_zone(photons=20000, t_stop=0.02, scale=10), launch=dict(blocks_per_sm=1, chunk=7))
+
+
+@pytest.mark.parametrize("name", ["three_region_g30_r2", "marshak", "hot_zone_s10"])
+@pytest.mark.parametrize("tuning", [
+    dict(scatter_batch=1, aggregate=0, tally_copies=1),    # the plain loop: sample at once, one atomic pair per lane
+    dict(scatter_batch=32, aggregate=1, tally_copies=1),   # scatters wait for a full warp; warp-aggregated deposits
+    dict(scatter_batch=5, aggregate=1, tally_copies=7),    # odd sizes; replicated tallies folded after the launch
+    dict(scatter_batch=12, aggregate=0, tally_copies=64),
+])
+def test_divergence_and_contention_knobs_do_not_change_results(name, tuning):
+    """Parking scatters, combining same-cell deposits inside a warp and replicating the tally array only regroup work
+    and reorder the tally sums: every per-photon integer stays bit-exact against the oracle, tallies within 1e-9."""
+    mk, n_ranks = CASES[name]
+    _run_cycles(mk(), n_ranks=n_ranks, tuning=tuning, max_cycles=3)
 
 
 def _aos_from(pre, seed):
