@@ -156,19 +156,34 @@ __global__ void __launch_bounds__(1024) k_scan_single(const uint32_t *__restrict
 }
 
 // results: [0] census_E, [1] exit_E ; counts -> stats[ST_N_CENSUS..]
+// The tile partials are summed by a fixed tree (thread t takes tiles t, t + 1024, ... in order, then a fixed warp /
+// block tree), so the result depends on the number of tiles only -- reproducible run to run.
 __global__ void __launch_bounds__(1024) k_scan_partials(uint32_t n_tiles, TilePartials T, double *results,
                                                         unsigned long long *stats) {
   single_cta_scan(T.n_census, n_tiles, T.tile_off);
+  __shared__ double s_ce[32], s_xe[32];
+  __shared__ unsigned long long s_nk[32], s_ne[32];
+  double ce = 0.0, xe = 0.0;
+  unsigned long long nk = 0, ne = 0;
+  for (uint32_t i = threadIdx.x; i < n_tiles; i += 1024) {
+    ce += T.census_E[i];
+    xe += T.exit_E[i];
+    nk += T.n_killed[i];
+    ne += T.n_exit[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ce += __shfl_down_sync(0xffffffffu, ce, o);
+    xe += __shfl_down_sync(0xffffffffu, xe, o);
+    nk += __shfl_down_sync(0xffffffffu, nk, o);
+    ne += __shfl_down_sync(0xffffffffu, ne, o);
+  }
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  if (lane == 0) { s_ce[w] = ce; s_xe[w] = xe; s_nk[w] = nk; s_ne[w] = ne; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double ce = 0.0, xe = 0.0;
-    unsigned long long nk = 0, ne = 0;
-    for (uint32_t i = 0; i < n_tiles; ++i) {
-      ce += T.census_E[i];
-      xe += T.exit_E[i];
-      nk += T.n_killed[i];
-      ne += T.n_exit[i];
-    }
+    ce = 0.0; xe = 0.0; nk = 0; ne = 0;
+    for (int i = 0; i < 32; ++i) { ce += s_ce[i]; xe += s_xe[i]; nk += s_nk[i]; ne += s_ne[i]; }
     results[0] = ce;
     results[1] = xe;
     stats[ST_N_CENSUS] = T.tile_off[n_tiles];
@@ -177,12 +192,19 @@ __global__ void __launch_bounds__(1024) k_scan_partials(uint32_t n_tiles, TilePa
   }
 }
 
+// Stable compaction of one tile: the ranks of the tile's CENSUS photons come from the same block scan as before; their
+// source indices are staged in shared memory in rank order, and the six 16-byte streams are then copied with one
+// thread per census photon, so the stores are fully coalesced (consecutive ranks -> consecutive addresses) and the
+// loads touch each surviving photon's sectors once.
 __global__ void __launch_bounds__(CT_THREADS) k_census_scatter(const uint8_t *__restrict__ desc, PhotonSoA src,
                                                                uint64_t n, PhotonSoA dst, uint64_t dst_offset,
                                                                const uint64_t *__restrict__ tile_off,
                                                                double census_life_dx) {
   __shared__ uint32_t s_warp[(CT_THREADS >> 5) + 1];
-  const uint64_t base = (uint64_t)blockIdx.x * CT_TILE + (uint64_t)threadIdx.x * CT_ITEMS;
+  __shared__ uint16_t s_idx[CT_TILE];  // offset inside the tile of the r-th census photon
+  const uint64_t tile_base = (uint64_t)blockIdx.x * CT_TILE;
+  const uint32_t tbase = threadIdx.x * CT_ITEMS;
+  const uint64_t base = tile_base + tbase;
   uint8_t d[CT_ITEMS];
   load_desc16(desc, base, n, d);
   uint32_t nc = 0;
@@ -190,22 +212,23 @@ __global__ void __launch_bounds__(CT_THREADS) k_census_scatter(const uint8_t *__
   for (int i = 0; i < CT_ITEMS; ++i) nc += (base + i < n && d[i] == EV_CENSUS) ? 1u : 0u;
   uint32_t tot;
   uint32_t r = block_excl_scan(nc, s_warp, &tot);
-  if (nc == 0) return;
-  uint64_t o = dst_offset + tile_off[blockIdx.x] + r;
-  const unsigned long long life_bits = (unsigned long long)__double_as_longlong(census_life_dx);
+  if (tot == 0) return;
 #pragma unroll
-  for (int i = 0; i < CT_ITEMS; ++i) {
-    if (base + i < n && d[i] == EV_CENSUS) {
-      const uint64_t s = base + i;
-      dst.xy[o] = src.xy[s];
-      dst.za[o] = src.za[s];
-      dst.bc[o] = src.bc[s];
-      dst.ee[o] = src.ee[s];
-      const ulonglong2 lc = src.lc[s];
-      dst.lc[o] = make_ulonglong2(life_bits, lc.y);  // life_dx = c * next_dt (src/post_process_functions.h:49)
-      dst.sg[o] = src.sg[s];
-      ++o;
-    }
+  for (int i = 0; i < CT_ITEMS; ++i)
+    if (base + i < n && d[i] == EV_CENSUS) s_idx[r++] = (uint16_t)(tbase + i);
+  __syncthreads();
+  const uint64_t o0 = dst_offset + tile_off[blockIdx.x];
+  const unsigned long long life_bits = (unsigned long long)__double_as_longlong(census_life_dx);
+  for (uint32_t j = threadIdx.x; j < tot; j += CT_THREADS) {
+    const uint64_t sidx = tile_base + s_idx[j], o = o0 + j;
+    const double2 xy = src.xy[sidx], za = src.za[sidx], bc = src.bc[sidx], ee = src.ee[sidx];
+    const ulonglong2 lc = src.lc[sidx], sg = src.sg[sidx];
+    dst.xy[o] = xy;
+    dst.za[o] = za;
+    dst.bc[o] = bc;
+    dst.ee[o] = ee;
+    dst.lc[o] = make_ulonglong2(life_bits, lc.y);  // life_dx = c * next_dt (src/post_process_functions.h:49)
+    dst.sg[o] = sg;
   }
 }
 

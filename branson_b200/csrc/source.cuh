@@ -54,11 +54,25 @@ struct SourceParams {
   double dt;
 };
 
-__device__ __forceinline__ void uniform_angle(uint64_t &ctr, uint64_t ctr_hi, uint64_t stream, double &ax, double &ay,
-                                              double &az) {
+// The (at most seven) draws of one new photon use the consecutive counters 0..7 of its own stream: they are evaluated
+// up front as two batches of four interleaved Threefry chains (rng.cuh) and handed out in the reference's draw order.
+struct Draws {
+  uint64_t w[8];
+  uint32_t used;
+  // `used` only ever holds values the compiler can enumerate, and the select chain keeps w[] in registers (a
+  // dynamically indexed array would live in local memory)
+  __device__ __forceinline__ double next() {
+    const uint32_t u = used++;
+    const uint64_t v = (u == 0) ? w[0] : (u == 1) ? w[1] : (u == 2) ? w[2] : (u == 3) ? w[3] : (u == 4) ? w[4]
+                     : (u == 5) ? w[5] : (u == 6) ? w[6] : w[7];
+    return u01_from_bits(v);
+  }
+};
+
+__device__ __forceinline__ void uniform_angle(Draws &D, double &ax, double &ay, double &az) {
   // src/sampling_functions.h:57-70
-  const double mu = rng_next(ctr, ctr_hi, stream) * 2.0 - 1.0;
-  const double phi = rng_next(ctr, ctr_hi, stream) * 2.0 * K_PI;
+  const double mu = D.next() * 2.0 - 1.0;
+  const double phi = D.next() * 2.0 * K_PI;
   const double sin_theta = sqrt(1.0 - mu * mu);
   double sp, cp;
   sincos(phi, &sp, &cp);
@@ -67,15 +81,29 @@ __device__ __forceinline__ void uniform_angle(uint64_t &ctr, uint64_t ctr_hi, ui
   az = mu;
 }
 
-__global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
-  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P.n) return;
-  // entry e with offsets[e] <= k < offsets[e+1]
-  uint32_t lo = 0, hi = P.n_entries;  // invariant: offsets[lo] <= k < offsets[hi]
-  while (hi - lo > 1) {
+// lower-bound search: entry e with offsets[e] <= k < offsets[e+1], inside [lo, hi)
+__device__ __forceinline__ uint32_t find_entry(const uint64_t *__restrict__ offsets, uint32_t lo, uint32_t hi, uint64_t k) {
+  while (hi - lo > 1) {  // invariant: offsets[lo] <= k < offsets[hi]
     const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&P.offsets[mid]) <= k) lo = mid; else hi = mid;
+    if (__ldg(&offsets[mid]) <= k) lo = mid; else hi = mid;
   }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
+  // The block's photons are consecutive, so their entries lie between the entry of its first and of its last photon:
+  // two threads search the whole table (20 dependent loads for 1.2e6 entries), everyone else only that window.
+  __shared__ uint32_t s_win[2];
+  const uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x;
+  const uint64_t k = k0 + threadIdx.x;
+  if (threadIdx.x == 0) s_win[0] = find_entry(P.offsets, 0, P.n_entries, k0);
+  if (threadIdx.x == 32) {
+    const uint64_t kl = (k0 + blockDim.x - 1 < P.n) ? k0 + blockDim.x - 1 : P.n - 1;
+    s_win[1] = find_entry(P.offsets, 0, P.n_entries, kl);
+  }
+  __syncthreads();
+  if (k >= P.n) return;
+  const uint32_t lo = find_entry(P.offsets, s_win[0], s_win[1] + 1, k);
   const uint32_t entry = lo;
   const uint32_t cell = (P.kinds == 2) ? (entry >> 1) : entry;
   const bool boundary_source = (P.kinds == 2) && (entry & 1u);
@@ -91,16 +119,18 @@ __global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
   const double y0 = __ldg(&fy[jj]), y1 = __ldg(&fy[jj + 1]);
   const double z0 = __ldg(&fz[kk]), z1 = __ldg(&fz[kk + 1]);
 
-  const uint64_t ctr_hi = P.ctr_hi;
   const uint64_t stream = P.stream_base + k;
-  uint64_t ctr = 0;
+  Draws D;
+  threefry2x64_20_w0_x4(0, P.ctr_hi, stream, D.w);
+  threefry2x64_20_w0_x4(4, P.ctr_hi, stream, D.w + 4);
+  D.used = 0;
   double x, y, z, ax, ay, az, life;
   if (!boundary_source) {
     // get_uniform_position_in_cell (src/sampling_functions.h:22-29)
-    x = x0 + rng_next(ctr, ctr_hi, stream) * (x1 - x0);
-    y = y0 + rng_next(ctr, ctr_hi, stream) * (y1 - y0);
-    z = z0 + rng_next(ctr, ctr_hi, stream) * (z1 - z0);
-    uniform_angle(ctr, ctr_hi, stream, ax, ay, az);
+    x = x0 + D.next() * (x1 - x0);
+    y = y0 + D.next() * (y1 - y0);
+    z = z0 + D.next() * (z1 - z0);
+    uniform_angle(D, ax, ay, az);
   } else {
     // Cell::get_source_face (src/cell.h:69-76): first face whose bc is SOURCE
     int face = -1;
@@ -113,20 +143,20 @@ __global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
     // get_uniform_position_on_face (src/sampling_functions.h:32-52)
     if (face == 0 || face == 1) {
       x = (face == 0) ? x0 : x1;
-      y = y0 + rng_next(ctr, ctr_hi, stream) * (y1 - y0);
-      z = z0 + rng_next(ctr, ctr_hi, stream) * (z1 - z0);
+      y = y0 + D.next() * (y1 - y0);
+      z = z0 + D.next() * (z1 - z0);
     } else if (face == 2 || face == 3) {
-      x = x0 + rng_next(ctr, ctr_hi, stream) * (x1 - x0);
+      x = x0 + D.next() * (x1 - x0);
       y = (face == 2) ? y0 : y1;
-      z = z0 + rng_next(ctr, ctr_hi, stream) * (z1 - z0);
+      z = z0 + D.next() * (z1 - z0);
     } else {
-      x = x0 + rng_next(ctr, ctr_hi, stream) * (x1 - x0);
-      y = y0 + rng_next(ctr, ctr_hi, stream) * (y1 - y0);
+      x = x0 + D.next() * (x1 - x0);
+      y = y0 + D.next() * (y1 - y0);
       z = (face == 4) ? z0 : z1;
     }
     // get_source_angle_on_face (src/sampling_functions.h:94-121), signs exactly as the reference has them
-    const double theta = acos(sqrt(rng_next(ctr, ctr_hi, stream)));
-    const double phi = rng_next(ctr, ctr_hi, stream) * 2.0 * K_PI;
+    const double theta = acos(sqrt(D.next()));
+    const double phi = D.next() * 2.0 * K_PI;
     const double sign = (face % 2) ? -1.0 : 1.0;
     double st, ct, sp, cp;
     sincos(theta, &st, &ct);
@@ -135,16 +165,16 @@ __global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
     else if (face == 2 || face == 3) { ax = st * sp; ay = ct; az = st * cp; }
     else { ax = st * cp; ay = st * sp; az = ct; }
   }
-  if (P.kinds == 2) life = rng_next(ctr, ctr_hi, stream) * K_C * P.dt;
+  if (P.kinds == 2) life = D.next() * K_C * P.dt;
   else life = K_C * P.dt;
-  const uint32_t group = (uint32_t)floor(rng_next(ctr, ctr_hi, stream) * (double)P.mesh.G);
+  const uint32_t group = (uint32_t)floor(D.next() * (double)P.mesh.G);
 
   const uint64_t o = P.dst_offset + k;
   P.ph.xy[o] = make_double2(x, y);
   P.ph.za[o] = make_double2(z, ax);
   P.ph.bc[o] = make_double2(ay, az);
   P.ph.ee[o] = make_double2(E, E);
-  P.ph.lc[o] = make_ulonglong2((unsigned long long)__double_as_longlong(life), ctr);
+  P.ph.lc[o] = make_ulonglong2((unsigned long long)__double_as_longlong(life), (unsigned long long)D.used);
   P.ph.sg[o] = make_ulonglong2(stream, (unsigned long long)cell | ((unsigned long long)group << 32));
 }
 
