@@ -221,6 +221,52 @@ def ncu_traffic():
     return None
 
 
+def aos_dropin_block(d, n_groups: int, device: int, repeats: int = 2):
+    """The literal drop-in for the reference's gpu_transport_photons(rank_cell_offset, std::vector<Photon>&, const Cell*,
+    std::vector<Cell_Tally>&) (src/history_based_transport.h:348-413), timed through the C ABI with HOST buffers: one call
+    of bgpu_transport_photons_aos on the next cycle's freshly sourced photons as 120-byte AoS records in host memory (both
+    PCIe directions of the photon list and of the tally array inside the timed region)."""
+    import numpy as np
+
+    from branson_b200 import gpu
+    f, op_a, op_s = d.array("f"), d.array("op_a"), d.array("op_s")
+    total_E = d.calculate_photon_energy()  # the next cycle's emission / source energies from the current temperatures
+    E_em, E_src = d.array("E_emission"), d.array("E_source")
+    nx, ny, nz = (int(d.param(k)) for k in ("nx", "ny", "nz"))
+    seed, n_user = int(d.param("seed")), int(d.param("n_user_photons"))
+    bc = ("REFLECT", "VACUUM", "REFLECT", "VACUUM", "VACUUM", "VACUUM")  # decks.hohlraum_single
+    ctx = gpu.Context(n_groups, nx, ny, nz, d.array("x_faces"), d.array("y_faces"), d.array("z_faces"), bc, seed,
+                      n_user, device=device)
+    try:
+        ctx.set_cell_data(f, op_a, op_s)
+        n_new, n_tot = ctx.source(int(d.param("step")), d.param("dt"), E_em, E_src, None, total_E)
+        soa = ctx.download(gpu.LIST_WORK)
+        aos0 = gpu.aos_from_soa(soa, seed)
+        del soa
+        best, hist = None, n_tot
+        for _ in range(repeats):
+            aos = aos0.copy()
+            tal = np.zeros((nx * ny * nz, 2))
+            t0 = time.perf_counter()
+            ctx.transport_photons_aos(aos, tal)
+            dt_s = time.perf_counter() - t0
+            best = dt_s if best is None else min(best, dt_s)
+        rec = aos.view(np.uint64).reshape(-1, 15)
+        desc = ((rec[:, 1] >> np.uint64(32)) & np.uint64(0xff)).astype(np.uint8)
+        assert not (desc == gpu.PASS).any(), "drop-in left photons unprocessed"
+        E_left = rec[:, 8].copy().view(np.float64)
+        e_in = rec[:, 9].copy().view(np.float64).sum()
+        e_out = tal[:, 0].sum() + E_left[desc != gpu.KILLED].sum()
+        return {"value": hist / best, "unit": UNIT, "photons": int(hist), "ms": 1e3 * best,
+                "h2d_bytes_per_step": int(120 * hist + 16 * nx * ny * nz),
+                "d2h_bytes_per_step": int(120 * hist + 16 * nx * ny * nz),
+                "rel_energy_balance": float(abs(e_in - e_out) / e_in),
+                "path": "bgpu_transport_photons_aos: the reference's std::vector<Photon> (120-byte AoS) and "
+                        "std::vector<Cell_Tally> in pageable host memory, updated in place (best of %d calls)" % repeats}
+    finally:
+        ctx.close()
+
+
 def our_arm(args):
     # host physics (calculate_photon_energy / update_temperature) is OpenMP: give each rank its share of the cores
     # (torchrun would otherwise pin every process to OMP_NUM_THREADS=1)
@@ -250,7 +296,9 @@ def our_arm(args):
         comm = driver.TorchComm(f"cuda:{local}")
 
     cycles = args.warmup + args.steps
-    deck = make_deck(world, cycles, photons_per_gpu=args.photons)
+    # one cycle more than is run, so that the state after the last timed cycle still has a time step ahead of it (the
+    # drop-in measurement below sources that next cycle's photons)
+    deck = make_deck(world, cycles + 1, photons_per_gpu=args.photons)
     tmp = tempfile.mkdtemp(prefix="branson_bench_")
     xml = deck.write(os.path.join(tmp, f"deck_rank{rank}.xml"))
     on_device = args.mesh == "device"
@@ -368,6 +416,11 @@ def our_arm(args):
                 "clocks": clocks,
                 "conservation": {"max_rel_radiation_balance": max(
                     abs(r["rad_balance_exact"]) / (r["pre_census_E"] + r["emission_E"] + r["source_E"]) for r in reps)}}
+        if world == 1 and not args.no_aos_dropin and (wall_host or not on_device):  # needs the host Mesh's current state
+            try:
+                line["e2e_aos_dropin"] = aos_dropin_block(d, N_GROUPS, local)
+            except Exception as e:
+                line["e2e_aos_dropin"] = {"value": None, "unit": UNIT, "path": f"failed: {type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_block(args.cpu_sample_photons)
@@ -391,6 +444,7 @@ def main():
     ap.add_argument("--photons", type=int, default=PHOTONS_PER_GPU, help="user photons per cycle per GPU")
     ap.add_argument("--algorithm", default="history", choices=["history", "event"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aos-dropin", action="store_true", help="skip the gpu_transport_photons drop-in measurement")
     ap.add_argument("--mesh", default="device", choices=["device", "host"],
                     help="where calculate_photon_energy / update_temperature run (e2e path)")
     ap.add_argument("--no-host-mesh-e2e", action="store_true", help="skip the second, host-mesh e2e measurement")

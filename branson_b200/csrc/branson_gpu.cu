@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/branson_gpu.h"
@@ -38,6 +40,7 @@ struct bgpu_ctx {
   int device = 0;
   int n_sm = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined AoS drop-in (created on first use)
   cudaEvent_t ev[6] = {};
   std::string err;
 
@@ -762,6 +765,8 @@ void bgpu_destroy(bgpu_ctx *c) {
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1145,19 +1150,123 @@ int bgpu_sync(bgpu_ctx *c) {
 void *bgpu_stream(bgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int bgpu_device(const bgpu_ctx *c) { return c ? c->device : -1; }
 
+namespace {
+
+PhotonSoA soa_view(const PhotonSoA &s, uint64_t off) {
+  PhotonSoA v = s;
+  v.xy += off; v.za += off; v.bc += off; v.ee += off; v.lc += off; v.sg += off;
+  v.cap = s.cap - off;
+  return v;
+}
+
+// Pipelined form of the drop-in (history algorithm, atomic tallies): the photon list goes through the device in
+// slices, so that the upload of slice j+1, the transport of slice j and the download of slice j-1 overlap.  Histories
+// are independent, so slicing changes nothing per photon; all slices accumulate into the same
+// tallies.  The uploads are issued by the calling thread and the downloads by a helper thread, because copies from /
+// to pageable host memory (a std::vector) block the thread that issues them.
+int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
+  if (!c->s_in) {
+    CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  }
+  // slices of at least 2^20 photons (enough to fill the persistent grid several times over), at most 8 of them
+  uint64_t m = std::max<uint64_t>(1ull << 20, (n + 7) / 8);
+  m = (m + 127) & ~127ull;
+  const uint32_t n_slices = (uint32_t)((n + m - 1) / m);
+  std::vector<cudaEvent_t> ev_in(n_slices), ev_done(n_slices);
+  for (uint32_t j = 0; j < n_slices; ++j) {
+    CU(c, cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming));
+  }
+  auto destroy_events = [&]() {
+    for (uint32_t j = 0; j < n_slices; ++j) { cudaEventDestroy(ev_in[j]); cudaEventDestroy(ev_done[j]); }
+  };
+  uint8_t *d_aos = (uint8_t *)c->scr_aos.p;
+  TransportParams P0 = make_params(c, true);
+  if (prepare_tally_copies(c)) { destroy_events(); return 1; }
+  if (c->tally_copies_live > 1) {
+    P0.tally_rep = (double2 *)c->scr_tally_rep.p;
+    P0.tally_copies = c->tally_copies_live;
+  }
+  std::atomic<uint32_t> issued{0};
+  std::atomic<int> abort_flag{0};
+  cudaError_t worker_err = cudaSuccess;
+  std::thread writer([&]() {
+    cudaError_t e = cudaSetDevice(c->device);
+    for (uint32_t j = 0; j < n_slices && e == cudaSuccess; ++j) {
+      while (issued.load(std::memory_order_acquire) <= j) {
+        if (abort_flag.load(std::memory_order_acquire)) return;
+        std::this_thread::yield();
+      }
+      const uint64_t off = (uint64_t)j * m, cnt = std::min<uint64_t>(m, n - off);
+      e = cudaEventSynchronize(ev_done[j]);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(photons + 120 * off, d_aos + 120 * off, 120 * cnt, cudaMemcpyDeviceToHost, c->s_out);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_out);
+    }
+    worker_err = e;
+  });
+  cudaError_t e = cudaSuccess;
+  for (uint32_t j = 0; j < n_slices && e == cudaSuccess; ++j) {
+    const uint64_t off = (uint64_t)j * m, cnt = std::min<uint64_t>(m, n - off);
+    e = cudaMemcpyAsync(d_aos + 120 * off, photons + 120 * off, 120 * cnt, cudaMemcpyHostToDevice, c->s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_in[j], c->s_in);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, ev_in[j], 0);
+    if (e != cudaSuccess) break;
+    const PhotonSoA view = soa_view(c->work, off);
+    c->launches += 2;  // + the history kernel, counted by launch_history
+    k_aos_to_soa<<<grid_for(cnt, 128), 128, 0, c->stream>>>((const uint64_t *)(d_aos + 120 * off), cnt, view, c->ctr_hi,
+                                                            c->d_stats);
+    TransportParams P = P0;
+    P.ph = view;
+    P.n = cnt;
+    P.desc = c->d_desc + off;
+    if (P.counters) P.counters += 4 * off;
+    e = cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream);
+    if (e == cudaSuccess && launch_history<TM_ATOMIC>(c, P)) e = cudaErrorUnknown;
+    k_soa_to_aos<<<grid_for(cnt, 128), 128, 0, c->stream>>>((uint64_t *)(d_aos + 120 * off), cnt, view, c->d_desc + off);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(ev_done[j], c->stream);
+    if (e == cudaSuccess) issued.store(j + 1, std::memory_order_release);
+  }
+  if (e != cudaSuccess) abort_flag.store(1, std::memory_order_release);
+  writer.join();
+  if (e == cudaSuccess && c->tally_copies_live > 1) {
+    ++c->launches;
+    k_fold_tally<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>((double2 *)c->d_tally, P0.tally_rep,
+                                                                          c->mesh.n_cells, c->tally_copies_live - 1);
+    e = cudaGetLastError();
+  }
+  destroy_events();
+  if (e != cudaSuccess) return fail(c, "bgpu_transport_photons_aos: %s", cudaGetErrorString(e));
+  if (worker_err != cudaSuccess) return fail(c, "bgpu_transport_photons_aos (download): %s", cudaGetErrorString(worker_err));
+  return 0;
+}
+
+}  // namespace
+
 int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cell_tallies, int algorithm,
                                int tally_mode) {
   if (!c || (!photons && n) || !cell_tallies) return fail(c, "bgpu_transport_photons_aos: null argument");
   CU(c, cudaSetDevice(c->device));
   const uint64_t nc = c->mesh.n_cells;
   if (n >= (1ull << 32)) return fail(c, "bgpu_transport_photons_aos: too many photons");
+  if (!c->have_cell_data) return fail(c, "bgpu_transport: cell data not set (call bgpu_set_cell_data first)");
   if (ensure_work(c, n, 0)) return 1;
   if (ensure(c, c->scr_aos, 120 * n)) return 1;
   CU(c, cudaMemcpyAsync(c->d_tally, cell_tallies, 16 * nc, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
   c->n_work = n;
   c->n_new = n;
-  if (n) {
+  const bool pipelined = algorithm == BGPU_HISTORY && tally_mode == BGPU_TALLY_ATOMIC && n >= (1ull << 21);
+  if (n && pipelined) {
+    if (transport_aos_pipelined(c, (uint8_t *)photons, n)) return 1;
+    unsigned long long bad = 0;
+    CU(c, cudaMemcpyAsync(&bad, c->d_stats + ST_BAD_RNG, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (bad)
+      return fail(c, "bgpu_transport_photons_aos: %llu photons carry an RNG seed/spawn word different from the ctx seed",
+                  bad);
+  } else if (n) {
     CU(c, cudaMemcpyAsync(c->scr_aos.p, photons, 120 * n, cudaMemcpyHostToDevice, c->stream));
     ++c->launches;
     k_aos_to_soa<<<grid_for(n, 128), 128, 0, c->stream>>>((const uint64_t *)c->scr_aos.p, n, c->work, c->ctr_hi,

@@ -266,6 +266,26 @@ class Context:
                                                   algorithm, tally_mode))
 
 
+def aos_from_soa(soa: dict, seed: int, source_type=None) -> np.ndarray:
+    """Pack photon arrays (the dict layout of Context.download) into the reference's 120-byte AoS `Photon` records
+    (src/photon.h:171-182): cell u32, group u32, source_type u32, descriptors u8[4], pos f64[3], angle f64[3], E, E0,
+    life_dx, RNG {ctr_lo, seed << 32, stream, 0}.  Returned as a flat uint8 array (what std::vector<Photon>::data() is)."""
+    n = len(soa["cell"])
+    rec = np.zeros((n, 15), np.uint64)
+    rec[:, 0] = soa["cell"].astype(np.uint64) | (soa["group"].astype(np.uint64) << np.uint64(32))
+    st = np.full(n, 2, np.uint64) if source_type is None else np.asarray(source_type).astype(np.uint64)
+    rec[:, 1] = st | (np.uint64(1) << np.uint64(32))  # descriptor PASS
+    rec[:, 2:5] = np.ascontiguousarray(soa["pos"], np.float64).reshape(n, 3).view(np.uint64)
+    rec[:, 5:8] = np.ascontiguousarray(soa["angle"], np.float64).reshape(n, 3).view(np.uint64)
+    rec[:, 8] = np.ascontiguousarray(soa["E"], np.float64).view(np.uint64)
+    rec[:, 9] = np.ascontiguousarray(soa["E0"], np.float64).view(np.uint64)
+    rec[:, 10] = np.ascontiguousarray(soa["life_dx"], np.float64).view(np.uint64)
+    rec[:, 11] = soa["ctr"]
+    rec[:, 12] = np.uint64(seed) << np.uint64(32)
+    rec[:, 13] = soa["stream"]
+    return rec.view(np.uint8).reshape(-1)
+
+
 def context_for_deck(deck, nodes, seed=None, n_user_photons=None, rank=0, n_ranks=1, device=-1, **kw) -> Context:
     nx, ny, nz = deck.n_cells_xyz
     xf, yf, zf = faces_from_nodes(nodes, nx, ny, nz)

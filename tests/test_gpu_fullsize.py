@@ -74,3 +74,37 @@ def test_big_cube_scaled(tmp_path):
     # configs[4] scaled to one GPU: 200^3 cells, 2e7 photons per cycle
     reps, _ = _run(decks.big_cube(n=200, photons=20_000_000, t_stop=0.002), tmp_path, 2)
     _check_balance(reps, 200 ** 3)
+
+
+def test_pipelined_aos_drop_in_equals_resident_path(tmp_path):
+    """bgpu_transport_photons_aos slices lists of >= 2^21 photons through the device (upload / transport / download
+    overlapped).  The same photons transported as one resident work list must give identical per-photon results
+    (integers and doubles bit for bit: nothing per photon depends on the slicing) and the same tallies to rounding."""
+    deck = decks.hot_zone(photons=2_400_000, t_stop=0.02)
+    d = driver.Driver(deck.write(str(tmp_path / "hz.xml")), n_groups=1, device=0, no_gpu=True)
+    total_E = d.calculate_photon_energy()
+    f, op_a, op_s = d.array("f"), d.array("op_a"), d.array("op_s")
+    nx, ny, nz = (int(d.param(k)) for k in ("nx", "ny", "nz"))
+    ctx = gpu.Context(1, nx, ny, nz, d.array("x_faces"), d.array("y_faces"), d.array("z_faces"), deck.bc, deck.seed,
+                      deck.photons, device=0)
+    ctx.enable_counters(True)  # validation mode: every photon's final state is written back
+    ctx.set_cell_data(f, op_a, op_s)
+    n_new, n_tot = ctx.source(1, d.param("dt"), d.array("E_emission"), d.array("E_source"), d.array("E_census"), total_E)
+    assert n_tot >= 1 << 21
+    pre = ctx.download(gpu.LIST_WORK)
+    aos = gpu.aos_from_soa(pre, deck.seed).copy()
+    ctx.transport(d.param("dt"))
+    post = ctx.download(gpu.LIST_WORK)
+    a, t, st = ctx.tallies()
+    tal = np.zeros((nx * ny * nz, 2))
+    ctx.transport_photons_aos(aos, tal)
+    rec = aos.view(np.uint64).reshape(-1, 15)
+    assert np.array_equal((rec[:, 0] & np.uint64(0xffffffff)).astype(np.uint32), post["cell"])
+    assert np.array_equal(((rec[:, 1] >> np.uint64(32)) & np.uint64(0xff)).astype(np.uint8), post["descriptor"])
+    assert np.array_equal(rec[:, 11], post["ctr"])
+    assert np.array_equal(rec[:, 8], post["E"].view(np.uint64))
+    assert np.array_equal(rec[:, 2:5].reshape(-1), post["pos"].view(np.uint64))
+    assert np.max(np.abs(tal[:, 0] - a)) <= 1e-12 * a.max()
+    assert np.max(np.abs(tal[:, 1] - t)) <= 1e-12 * t.max()
+    ctx.close()
+    d.close()

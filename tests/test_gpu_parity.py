@@ -225,19 +225,7 @@ def test_divergence_and_contention_knobs_do_not_change_results(name, tuning):
 
 
 def _aos_from(pre, seed):
-    n = len(pre["cell"])
-    rec = np.zeros((n, 15), np.uint64)
-    rec[:, 0] = pre["cell"].astype(np.uint64) | (pre["group"].astype(np.uint64) << np.uint64(32))
-    rec[:, 1] = pre["source_type"].astype(np.uint64) | (np.uint64(1) << np.uint64(32))  # descriptor PASS
-    rec[:, 2:5] = pre["pos"].reshape(n, 3).view(np.uint64)
-    rec[:, 5:8] = pre["angle"].reshape(n, 3).view(np.uint64)
-    rec[:, 8] = pre["E"].view(np.uint64)
-    rec[:, 9] = pre["E0"].view(np.uint64)
-    rec[:, 10] = pre["life_dx"].view(np.uint64)
-    rec[:, 11] = pre["ctr"]
-    rec[:, 12] = np.uint64(seed) << np.uint64(32)
-    rec[:, 13] = pre["stream"]
-    return rec.view(np.uint8).reshape(-1).copy()
+    return gpu.aos_from_soa(pre, seed, source_type=pre["source_type"]).copy()
 
 
 @pytest.mark.parametrize("tally_mode", [gpu.TALLY_ATOMIC, gpu.TALLY_DETERMINISTIC])
