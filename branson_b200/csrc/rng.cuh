@@ -51,40 +51,51 @@ __device__ __forceinline__ uint64_t threefry2x64_20_w0(uint64_t ctr_lo, uint64_t
   return x0;
 }
 
-// Four consecutive counters at once: ctr_lo + 0..3.  The four Threefry evaluations are independent, so the fully
-// unrolled rounds interleave into four dependency chains (the single-draw form is one serial chain of ~135 integer
-// instructions and leaves the ALU pipe waiting on its own latency).
-__device__ __forceinline__ void threefry2x64_20_w0_x4(uint64_t ctr_lo, uint64_t ctr_hi, uint64_t k0, uint64_t w[4]) {
+// N counters of one stream at once: ctr_lo + OFF[j].  The Threefry evaluations are independent, so the fully unrolled
+// rounds interleave into N dependency chains (the single-draw form is one serial chain of ~135 integer instructions
+// and leaves the ALU pipe waiting on its own latency).
+template <int N>
+__device__ __forceinline__ void threefry2x64_20_w0_multi(uint64_t ctr_lo, uint64_t ctr_hi, uint64_t k0,
+                                                         const int (&OFF)[N], uint64_t (&w)[N]) {
   const uint64_t ks0 = k0;
   const uint64_t ks2 = 0x1BD11BDAA9FC1A22ULL ^ k0;
-  uint64_t x0[4], x1[4];
+  uint64_t x0[N], x1[N];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    x0[j] = ctr_lo + (uint64_t)j + ks0;
+  for (int j = 0; j < N; ++j) {
+    x0[j] = ctr_lo + (uint64_t)OFF[j] + ks0;
     x1[j] = ctr_hi;
   }
-#define BG_TF_ROUND4(R)            \
-  _Pragma("unroll") for (int j = 0; j < 4; ++j) { \
+#define BG_TF_ROUNDN(R)            \
+  _Pragma("unroll") for (int j = 0; j < N; ++j) { \
     x0[j] += x1[j];                \
     x1[j] = rotl64(x1[j], (R));    \
     x1[j] ^= x0[j];                \
   }
-  BG_TF_ROUND4(16) BG_TF_ROUND4(42) BG_TF_ROUND4(12) BG_TF_ROUND4(31)
+  BG_TF_ROUNDN(16) BG_TF_ROUNDN(42) BG_TF_ROUNDN(12) BG_TF_ROUNDN(31)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) x1[j] += ks2 + 1;
-  BG_TF_ROUND4(16) BG_TF_ROUND4(32) BG_TF_ROUND4(24) BG_TF_ROUND4(21)
+  for (int j = 0; j < N; ++j) x1[j] += ks2 + 1;
+  BG_TF_ROUNDN(16) BG_TF_ROUNDN(32) BG_TF_ROUNDN(24) BG_TF_ROUNDN(21)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { x0[j] += ks2; x1[j] += ks0 + 2; }
-  BG_TF_ROUND4(16) BG_TF_ROUND4(42) BG_TF_ROUND4(12) BG_TF_ROUND4(31)
+  for (int j = 0; j < N; ++j) { x0[j] += ks2; x1[j] += ks0 + 2; }
+  BG_TF_ROUNDN(16) BG_TF_ROUNDN(42) BG_TF_ROUNDN(12) BG_TF_ROUNDN(31)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { x0[j] += ks0; x1[j] += 3; }
-  BG_TF_ROUND4(16) BG_TF_ROUND4(32) BG_TF_ROUND4(24) BG_TF_ROUND4(21)
+  for (int j = 0; j < N; ++j) { x0[j] += ks0; x1[j] += 3; }
+  BG_TF_ROUNDN(16) BG_TF_ROUNDN(32) BG_TF_ROUNDN(24) BG_TF_ROUNDN(21)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) x1[j] += ks2 + 4;
-  BG_TF_ROUND4(16) BG_TF_ROUND4(42) BG_TF_ROUND4(12) BG_TF_ROUND4(31)
+  for (int j = 0; j < N; ++j) x1[j] += ks2 + 4;
+  BG_TF_ROUNDN(16) BG_TF_ROUNDN(42) BG_TF_ROUNDN(12) BG_TF_ROUNDN(31)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) w[j] = x0[j] + ks2;
-#undef BG_TF_ROUND4
+  for (int j = 0; j < N; ++j) w[j] = x0[j] + ks2;
+#undef BG_TF_ROUNDN
+}
+
+// Four consecutive counters: ctr_lo + 0..3.
+__device__ __forceinline__ void threefry2x64_20_w0_x4(uint64_t ctr_lo, uint64_t ctr_hi, uint64_t k0, uint64_t w[4]) {
+  const int off[4] = {0, 1, 2, 3};
+  uint64_t v[4];
+  threefry2x64_20_w0_multi<4>(ctr_lo, ctr_hi, k0, off, v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) w[j] = v[j];
 }
 
 // General form (arbitrary key high word), used by the known-answer test kernel.

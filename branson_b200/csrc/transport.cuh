@@ -282,13 +282,38 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
 // The scatter event (:94-101).  Its draws use consecutive counters, so they are evaluated as four interleaved
 // Threefry chains: mu, phi (src/sampling_functions.h:57-70), the effective-scatter test (:98) and -- if it passes -- the
 // group CDF value (src/sampling_functions.h:126-138).  An unused fourth value is discarded, its counter not consumed.
-__device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
-  uint64_t w[4];
-  threefry2x64_20_w0_x4(S.ctr, C.ctr_hi, S.stream, w);
+__device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const unsigned lanes) {
+  // Draws of a scatter, at consecutive counters: mu, phi (get_uniform_angle), the physical-vs-effective test (:98), and
+  // -- if effective -- the group CDF value (sample_emission_group).  Two of them can be void:
+  //   * with sigma_s == 0 the test is `u > 0`, true for every u01 value (u >= 2^-53): the draw is consumed (the counter
+  //     advances) but its value cannot matter, so it is not evaluated when no lane of the warp has sigma_s != 0;
+  //   * with one group the walk returns g = 0 for every c in (0,1): abs[0] * fl(1 / abs[0]) is 1 or 1 - 2^-53, and
+  //     u01 <= 1 - 2^-53, so the first subtraction already ends the loop -- the CDF draw is consumed, not evaluated.
+  // Every reference deck has sigma_s == 0: an effective scatter then costs 3 Threefry evaluations (2 on gray decks)
+  // instead of 4, with bit-identical results and counters.
+  const bool test_void = !__any_sync(lanes, S.sig_s != 0.0);
+  const bool cdf_void = C.G == 1u;
+  uint64_t w_mu, w_phi, w_test = ~0ull, w_cdf = 0ull;
+  if (test_void && cdf_void) {
+    const int off[2] = {0, 1};
+    uint64_t w[2];
+    threefry2x64_20_w0_multi<2>(S.ctr, C.ctr_hi, S.stream, off, w);
+    w_mu = w[0]; w_phi = w[1];
+  } else if (test_void) {
+    const int off[3] = {0, 1, 3};
+    uint64_t w[3];
+    threefry2x64_20_w0_multi<3>(S.ctr, C.ctr_hi, S.stream, off, w);
+    w_mu = w[0]; w_phi = w[1]; w_cdf = w[2];
+  } else {
+    const int off[4] = {0, 1, 2, 3};
+    uint64_t w[4];
+    threefry2x64_20_w0_multi<4>(S.ctr, C.ctr_hi, S.stream, off, w);
+    w_mu = w[0]; w_phi = w[1]; w_test = w[2]; w_cdf = w[3];
+  }
   S.ctr += 3;
   ++S.c_sc;
-  const double mu = u01_from_bits(w[0]) * 2.0 - 1.0;
-  const double phi = u01_from_bits(w[1]) * 2.0 * K_PI;
+  const double mu = u01_from_bits(w_mu) * 2.0 - 1.0;
+  const double phi = u01_from_bits(w_phi) * 2.0 * K_PI;
   const double sin_theta = sqrt(1.0 - mu * mu);
   double sp, cp;
 #if BG_FM_SINCOS
@@ -301,10 +326,16 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C) {
   S.az = mu;
   // physical vs effective scatter (src/history_based_transport.h:98-100)
   // sigma_s == 0 (every reference deck): 0 / x is exactly +0, no division needed
-  const double p_phys = (S.sig_s == 0.0) ? 0.0 : S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s);
-  if (!(u01_from_bits(w[2]) > p_phys)) return;
-  double cdf = u01_from_bits(w[3]);
+  if (!test_void) {
+    const double p_phys = (S.sig_s == 0.0) ? 0.0 : S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s);
+    if (!(u01_from_bits(w_test) > p_phys)) return;
+  }
   S.ctr += 1;
+  if (cdf_void) {  // g = 0 = the photon's group: nothing changes
+    S.gmask |= 1u;
+    return;
+  }
+  double cdf = u01_from_bits(w_cdf);
   const uint32_t G = C.G;
   int g = -1;
   if (C.uniform_groups && G <= 512) {
@@ -582,7 +613,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
       const unsigned movable = __ballot_sync(FULL, active && !pending_scatter);
       if ((uint32_t)__popc(parked) >= scatter_batch || movable == 0u) {
         if (pending_scatter) {
-          scatter_event(S, C);
+          scatter_event(S, C, parked);
           pending_scatter = false;
         }
       }
