@@ -183,16 +183,22 @@ template <class Deposit>
 __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uint32_t bcpack, Deposit &&deposit,
                                              uint8_t &descriptor, const unsigned lanes) {
   const double total_sigma_s = (1.0 - S.f) * S.sig_a + S.sig_s;
-  double d_scat = 1.0e100;
-  if (total_sigma_s > 0.0) {
+  // Distance to the next collision (:62-63).  The reference draws only if total_sigma_s > 0; here the Threefry block is
+  // evaluated unconditionally and the draw merely *consumed* under that condition (the counter decides what the stream
+  // yields next, not the evaluation), which keeps this long dependent integer chain in one basic block with the
+  // boundary distances below, so the FP64 divisions fill its latency.  (total_sigma_s > 0 in every reference deck.)
+  double d_scat;
+  {
     const uint64_t w = threefry2x64_20_w0(S.ctr, C.ctr_hi, S.stream);
-    S.ctr += 1;
+    const bool collide = total_sigma_s > 0.0;
+    S.ctr += collide ? 1u : 0u;
 #if BG_FM_LOG
     // -log(u) / sigma with u = ((w >> 11) | 1) 2^-53 (rng.cuh u01_from_bits): the 2^-53 goes into the exponent
-    d_scat = -fm_log_pos_scaled(__ull2double_rn((w >> 11) | 1ULL), -53) / total_sigma_s;
+    const double dd = -fm_log_pos_scaled(__ull2double_rn((w >> 11) | 1ULL), -53) / total_sigma_s;
 #else
-    d_scat = -log(u01_from_bits(w)) / total_sigma_s;
+    const double dd = -log(u01_from_bits(w)) / total_sigma_s;
 #endif
+    d_scat = collide ? dd : 1.0e100;
   }
 
   // distance to boundary: strict-minimum scan over x, y, z starting from 1e16 (src/cell.h:116-132)
