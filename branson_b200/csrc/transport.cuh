@@ -30,6 +30,14 @@
 #ifndef BG_FM_SINCOS
 #define BG_FM_SINCOS 1
 #endif
+#ifndef BG_FM_DIV
+#define BG_FM_DIV 1
+#endif
+#if BG_FM_DIV
+#define BG_DIV(a, b) fm_div((a), (b))
+#else
+#define BG_DIV(a, b) ((a) / (b))
+#endif
 
 namespace bg {
 
@@ -194,7 +202,7 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
     S.ctr += collide ? 1u : 0u;
 #if BG_FM_LOG
     // -log(u) / sigma with u = ((w >> 11) | 1) 2^-53 (rng.cuh u01_from_bits): the 2^-53 goes into the exponent
-    const double dd = -fm_log_pos_scaled(__ull2double_rn((w >> 11) | 1ULL), -53) / total_sigma_s;
+    const double dd = BG_DIV(-fm_log_pos_scaled(__ull2double_rn((w >> 11) | 1ULL), -53), total_sigma_s);
 #else
     const double dd = -log(u01_from_bits(w)) / total_sigma_s;
 #endif
@@ -205,9 +213,9 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
   double d_bnd = 1.0e16;
   {
     const bool px = 0.0 < S.ax, py = 0.0 < S.ay, pz = 0.0 < S.az;
-    const double dx = (C.fx[S.i + (px ? 1 : 0)] - S.x) / S.ax;
-    const double dy = (C.fy[S.j + (py ? 1 : 0)] - S.y) / S.ay;
-    const double dz = (C.fz[S.k + (pz ? 1 : 0)] - S.z) / S.az;
+    const double dx = BG_DIV(C.fx[S.i + (px ? 1 : 0)] - S.x, S.ax);
+    const double dy = BG_DIV(C.fy[S.j + (py ? 1 : 0)] - S.y, S.ay);
+    const double dz = BG_DIV(C.fz[S.k + (pz ? 1 : 0)] - S.z, S.az);
     if (dx < d_bnd) { d_bnd = dx; S.surface = px ? 1u : 0u; }
     if (dy < d_bnd) { d_bnd = dy; S.surface = 2u + (py ? 1u : 0u); }
     if (dz < d_bnd) { d_bnd = dz; S.surface = 4u + (pz ? 1u : 0u); }
@@ -222,7 +230,7 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
   const double absorbed = S.E * (1.0 - exp(-S.sig_a * S.f * d));
 #endif
   S.loc_abs += absorbed;
-  S.loc_trk += absorbed / (S.sig_a * S.f);
+  S.loc_trk += BG_DIV(absorbed, S.sig_a * S.f);
   S.E = S.E - absorbed;
   S.x += S.ax * d;
   S.y += S.ay * d;
@@ -232,7 +240,7 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
   int r = R_CONTINUE;
   bool dep = false, crossed = false;
   const uint32_t dep_cell = S.cell;
-  if (S.E / S.E0 < K_CUTOFF) {  // energy cutoff first (:85-91)
+  if (BG_DIV(S.E, S.E0) < K_CUTOFF) {  // energy cutoff first (:85-91)
     S.loc_abs += S.E;
     dep = true;
     descriptor = EV_KILLED;

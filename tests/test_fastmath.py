@@ -102,3 +102,22 @@ def test_device_build_against_glibc():
     # no worse than libdevice's sincos on the same arguments
     cs, cc = gpu.fastmath("cuda_sincos", phi)
     assert np.mean(s == ws) >= np.mean(cs == ws) - 0.02 and np.mean(c == wc) >= np.mean(cc == wc) - 0.02
+
+
+@pytest.mark.gpu
+def test_device_division_is_ieee_on_the_loop_ranges():
+    """fm_div (the compiler's division fast path without its range test) against IEEE division: bit for bit."""
+    from branson_b200 import gpu
+    rng = np.random.default_rng(23)
+    n = 4_000_000
+    x = rng.standard_normal(n) * 10.0 ** rng.uniform(-100, 100, n)
+    x[: n // 4] = rng.uniform(-1, 1, n // 4)            # direction cosines, face distances
+    x[n // 4: n // 2: 2] = 0.0                          # zero numerators (photon on a face, absorbed == 0)
+    got = gpu.fastmath("div", x)
+    den = x.reshape(-1, 2)[:, ::-1].reshape(-1)
+    ok = den != 0.0
+    want = x[ok] / den[ok]
+    bad = got[ok].view(np.uint64) != want.view(np.uint64)
+    assert not bad.any(), (int(bad.sum()), x[ok][bad][:5], den[ok][bad][:5])
+    # a zero divisor gives NaN where IEEE gives +-inf (or NaN): every consumer in the loop is a `d < d_min` test
+    assert not np.isfinite(got[~ok]).any()
