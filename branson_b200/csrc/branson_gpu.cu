@@ -1450,11 +1450,12 @@ __global__ void k_threefry_kat(const uint64_t *in, uint64_t *out) {
   threefry2x64_20(in, in + 2, out);
 }
 // accuracy hook for fastmath.cuh: which = 0 exp, 1 log, 2 sincos (out = sin, out2 = cos), 3 libdevice sincos,
-// 4 division: in[i] / in[i ^ 1] (neighbouring entries paired)
+// 4 division: in[i] / in[i ^ 1] (neighbouring entries paired), 5 square root
 __global__ void k_fastmath(int which, uint64_t n, const double *in, double *out, double *out2) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const double x = in[i];
     if (which == 4) out[i] = ((i ^ 1) < n) ? fm_div(x, in[i ^ 1]) : 0.0;
+    else if (which == 5) out[i] = fm_sqrt(x);
     else if (which == 0) out[i] = fm_exp_flush(x);
     else if (which == 1) out[i] = fm_log_pos(x);
     else if (which == 2) fm_sincos(x, &out[i], &out2[i]);

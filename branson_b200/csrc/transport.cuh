@@ -328,7 +328,11 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const un
   ++S.c_sc;
   const double mu = u01_from_bits(w_mu) * 2.0 - 1.0;
   const double phi = u01_from_bits(w_phi) * 2.0 * K_PI;
+#if BG_FM_DIV
+  const double sin_theta = fm_sqrt(1.0 - mu * mu);  // mu in (-1, 1): the argument is a normal number
+#else
   const double sin_theta = sqrt(1.0 - mu * mu);
+#endif
   double sp, cp;
 #if BG_FM_SINCOS
   fm_sincos(phi, &sp, &cp);

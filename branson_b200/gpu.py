@@ -311,10 +311,10 @@ def threefry(ctr, key):
 
 def fastmath(which, x):
     """csrc/fastmath.cuh on the device: which = "exp" | "log" | "sincos" | "cuda_sincos" (the last: libdevice) | "div"
-    (out[i] = x[i] / x[i ^ 1]: neighbouring entries are paired, even length)."""
+    (out[i] = x[i] / x[i ^ 1]: neighbouring entries are paired, even length) | "sqrt"."""
     x = np.ascontiguousarray(x, np.float64)
     out, out2 = np.zeros_like(x), np.zeros_like(x)
-    code = {"exp": 0, "log": 1, "sincos": 2, "cuda_sincos": 3, "div": 4}[which]
+    code = {"exp": 0, "log": 1, "sincos": 2, "cuda_sincos": 3, "div": 4, "sqrt": 5}[which]
     if lib().bgpu_test_fastmath(code, x.size, _ptr(x), _ptr(out), _ptr(out2)):
         raise GpuError("bgpu_test_fastmath failed")
     return (out, out2) if code in (2, 3) else out

@@ -121,3 +121,8 @@ def test_device_division_is_ieee_on_the_loop_ranges():
     assert not bad.any(), (int(bad.sum()), x[ok][bad][:5], den[ok][bad][:5])
     # a zero divisor gives NaN where IEEE gives +-inf (or NaN): every consumer in the loop is a `d < d_min` test
     assert not np.isfinite(got[~ok]).any()
+    # fm_sqrt: the compiler's square-root fast path; the loop's arguments are 1 - mu^2 in [2^-51, 1]
+    a = np.concatenate([1.0 - (2.0 * rng.random(n) - 1.0) ** 2, 2.0 ** rng.uniform(-52, 1, n // 4),
+                        10.0 ** rng.uniform(-100, 100, n // 4)])
+    a = a[a > 0]
+    assert np.array_equal(gpu.fastmath("sqrt", a).view(np.uint64), np.sqrt(a).view(np.uint64))
