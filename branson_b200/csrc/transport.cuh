@@ -362,7 +362,7 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const un
     // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
     // clear zero by a margin far above that bound, the sequential result is provably k0 -- no loads, no dependent
     // chain, no divergence over the walk length.  Otherwise (probability ~1e-11 per scatter) fall through to the walk.
-    if (S.p_grp == 0.0) S.p_grp = S.sig_a * (1.0 / (S.sig_a * (double)G));
+    if (S.p_grp == 0.0) S.p_grp = S.sig_a * BG_DIV(1.0, S.sig_a * (double)G);
     const int k0 = (int)(cdf * (double)G);
     const double before = fma(-(double)k0, S.p_grp, cdf);  // c_k0 up to rounding
     const double after = before - S.p_grp;                  // c_(k0+1)
