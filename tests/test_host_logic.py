@@ -190,3 +190,23 @@ def test_time_stepping_equals_oracle(tmp_path):
         d.next_time_step()
         n += 1
     assert d.finished() and n == deck.n_cycles() and d.param("step") == n + 1
+
+
+def test_aos_record_layout_matches_the_reference_photon():
+    """gpu.aos_from_soa builds the reference's 120-byte Photon (src/photon.h:171-182: cell_ID u32, group u32, source_type
+    u32, descriptors u8[4], pos f64[3], angle f64[3], E, E0, life_dx, RNG {ctr_lo, seed << 32, stream, 0}); the byte
+    offsets are what bgpu_transport_photons_aos reads and writes (csrc/branson_gpu.cu k_aos_to_soa / k_soa_to_aos)."""
+    import struct
+
+    from branson_b200 import gpu
+    soa = dict(cell=np.array([7, 9], np.uint32), group=np.array([3, 29], np.uint32),
+               pos=np.array([.1, .2, .3, .4, .5, .6]), angle=np.array([1., 0., 0., 0., 0., -1.]),
+               E=np.array([2.5, 3.5]), E0=np.array([4.5, 5.5]), life_dx=np.array([.7, .8]),
+               ctr=np.array([11, 12], np.uint64), stream=np.array([10 ** 13 + 5, 10 ** 13 + 6], np.uint64))
+    b = gpu.aos_from_soa(soa, seed=14706, source_type=np.array([2, 1])).tobytes()
+    assert len(b) == 240
+    rec = struct.unpack("<III4B3d3d3d4Q", b[120:])
+    assert rec[:3] == (9, 29, 1) and rec[3] == gpu.PASS
+    assert rec[7:10] == (.4, .5, .6) and rec[10:13] == (0., 0., -1.)
+    assert rec[13:16] == (3.5, 5.5, .8)
+    assert rec[16:] == (12, 14706 << 32, 10 ** 13 + 6, 0)
