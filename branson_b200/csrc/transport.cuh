@@ -472,7 +472,9 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   C.nx = P.mesh.nx; C.ny = P.mesh.ny; C.nz = P.mesh.nz; C.G = P.mesh.G;
   C.sxy = C.nx * C.ny;
   C.f = P.f; C.opa = P.opa; C.ops = P.ops;
-  C.ctr_hi = P.ctr_hi;
+  // the counter's high word is seed << 32 (src/RNG.h:318-330): rebuilt from its upper half so that the compiler knows the
+  // low 32 bits are zero and folds them out of the first Threefry round
+  C.ctr_hi = (uint64_t)(uint32_t)(P.ctr_hi >> 32) << 32;
   C.uniform_groups = P.uniform_groups != 0;
   C.inv_sxy = P.inv_sxy; C.inv_nx = P.inv_nx;
   const unsigned FULL = 0xffffffffu;
