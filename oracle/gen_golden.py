@@ -34,9 +34,27 @@ def golden_cases():
     }
 
 
+def comb_cases():
+    """name -> (deck, cycles, max_census_photons, rng stream): comb_photons (reference src/census_functions.h:48-93) run
+    by the unmodified reference on the census left after `cycles` cycles."""
+    return {
+        "comb_hot_zone_s10": (decks.hot_zone(photons=30000, t_stop=0.03, scale=10), 3, 1000, 9 * 10 ** 12),
+        "comb_three_region_g30": (decks.simple_three_region(photons=20000, n_groups=30), 2, 60, 9 * 10 ** 12 + 1),
+    }
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    for name, (deck, cycles, max_census, stream) in comb_cases().items():
+        dumps, _ = refio.run_reference(deck, max_cycles=cycles, photon_limit=0, comb_max=max_census, comb_stream=stream)
+        flat = {k: v for k, v in dumps[0].items() if k.startswith("comb/") or k in ("seed", "n_cells")}
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **flat)
+        print(f"{name}: census {len(flat['comb/pre/cell'])} -> {len(flat['comb/post/cell'])}, "
+              f"{os.path.getsize(path) / 1e3:.0f} kB")
+    if "--comb-only" in sys.argv:
+        return
     for name, (deck, n_ranks) in golden_cases().items():
         dumps, _ = refio.run_reference(deck, n_ranks=n_ranks, photon_limit=PHOTON_LIMIT)
         flat = {}

@@ -1000,3 +1000,43 @@ int orc_cycle(orc_sim *s, int keep_photons) {
 }
 
 double orc_last_transport_seconds(const orc_sim *s) { return s->transport_seconds; }
+
+/* ------------------------------------------------------------------------ */
+/* comb_photons, reference src/census_functions.h:48-93.  The reference keeps three unordered_maps keyed by cell; plain
+ * arrays indexed by cell hold the same values (every update is keyed, nothing iterates over the maps). */
+uint64_t orc_comb_photons(uint64_t n, const uint32_t *cell, const double *E, double global_census_E,
+                          int64_t max_census_photons, uint64_t rng_state[4], uint8_t *keep, double *new_E) {
+  uint32_t max_cell = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    if (cell[i] > max_cell) max_cell = cell[i];
+  uint32_t *count = (uint32_t *)xcalloc((size_t)max_cell + 1, 4);
+  double *cell_E = (double *)xcalloc((size_t)max_cell + 1, 8);
+  double *corrected = (double *)xcalloc((size_t)max_cell + 1, 8);
+  const double comb_photon_E = global_census_E / (double)max_census_photons; /* :65 */
+  for (uint64_t i = 0; i < n; ++i) {                                         /* :67-70 */
+    count[cell[i]]++;
+    cell_E[cell[i]] += E[i];
+  }
+  uint64_t kept = 0;
+  for (uint64_t i = 0; i < n; ++i) { /* :72-85 */
+    const uint32_t c = cell[i];
+    const double p_kill = 1.0 - E[i] / comb_photon_E;
+    const double rand_check = orc_rng_next(rng_state);
+    if (rand_check > p_kill || count[c] == 1) {
+      keep[i] = 1;
+      corrected[c] += comb_photon_E;
+      ++kept;
+    } else {
+      keep[i] = 0;
+      count[c]--;
+    }
+  }
+  for (uint64_t i = 0; i < n; ++i) { /* :88-93 */
+    const uint32_t c = cell[i];
+    new_E[i] = keep[i] ? comb_photon_E + (cell_E[c] - corrected[c]) / (double)count[c] : 0.0;
+  }
+  free(count);
+  free(cell_E);
+  free(corrected);
+  return kept;
+}

@@ -82,6 +82,14 @@ int orc_transport_list(orc_sim *s, int rank, uint64_t n, uint32_t *cell, uint32_
                        const uint64_t *stream, uint8_t *descriptor, double *abs_E, double *track_E,
                        uint32_t *counters);
 
+/* Population control of the census: reference census_functions.h:48-93 (comb_photons; defined but never called in
+ * this snapshot).  cell[n], E[n] = the census in list order; global_census_E = the all-reduced census energy (:61-64;
+ * for one rank: the in-order sum of E); rng_state advances by one draw per photon (:76).  Outputs: keep[n] = 1 for the
+ * photons that survive (their list order is preserved, :79), new_E[n] = their corrected energy (:86-90).  Returns the
+ * number kept. */
+uint64_t orc_comb_photons(uint64_t n, const uint32_t *cell, const double *E, double global_census_E,
+                          int64_t max_census_photons, uint64_t rng_state[4], uint8_t *keep, double *new_E);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,3 +176,22 @@ def uniform_angle(seed: int, stream: int):
     a = np.zeros(3)
     lib().orc_uniform_angle(_ptr(st), _ptr(a))
     return a
+
+
+def comb_photons(cell, E, global_census_E: float, max_census_photons: int, seed: int, stream: int):
+    """reference census_functions.h:48-93 on a census given as arrays; returns (keep mask, corrected energies of the
+    kept photons, RNG draws consumed)."""
+    cell = np.ascontiguousarray(cell, np.uint32)
+    E = np.ascontiguousarray(E, np.float64)
+    n = len(cell)
+    st = np.zeros(4, np.uint64)
+    lib().orc_rng_init(_ptr(st), seed, stream)
+    keep, new_E = np.zeros(n, np.uint8), np.zeros(n)
+    L = lib()
+    L.orc_comb_photons.restype = C.c_uint64
+    L.orc_comb_photons.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]
+    kept = L.orc_comb_photons(n, _ptr(cell), _ptr(E), float(global_census_E), int(max_census_photons), _ptr(st),
+                              _ptr(keep), _ptr(new_E))
+    assert kept == int(keep.sum())
+    return keep.astype(bool), new_E[keep.astype(bool)], int(st[0])

@@ -54,6 +54,7 @@
 #include "input.h"
 #include "mesh.h"
 #include "mpi_types.h"
+#include "census_functions.h"
 #include "replicated_driver.h"
 #include "timer.h"
 #undef private
@@ -291,6 +292,34 @@ int main(int argc, char **argv) {
       imc_state.print_conservation(imc_p.get_dd_mode());
       imc_state.next_time_step();
       ++cycles_done;
+    }
+    // Optional: the reference's population control, which exists as a function (src/census_functions.h:48-93) but has
+    // no call site in this snapshot.  Run it once on the final census with RNG(seed, REF_COMB_STREAM) and dump the list
+    // before and after, as the function-level oracle of the device comb.
+    if (const char *cm = std::getenv("REF_COMB_MAX")) {
+      const int64_t max_census = std::atoll(cm);
+      const char *cs = std::getenv("REF_COMB_STREAM");
+      const uint64_t stream = cs ? std::strtoull(cs, nullptr, 10) : 0ull;
+      RNG rng(seed, stream);
+      dump_photons(d, "comb/pre/", census_photons, ~size_t(0), false);
+      {
+        std::vector<uint64_t> st(census_photons.size());
+        std::vector<double> e0(census_photons.size());
+        for (size_t i = 0; i < st.size(); ++i) { st[i] = census_photons[i].m_rng.data[2]; e0[i] = census_photons[i].m_E0; }
+        d.u64("comb/pre/stream", st);
+        d.f64("comb/pre/E0", e0);
+      }
+      d.f64("comb/local_census_E", get_photon_list_E(census_photons));
+      d.u64("comb/max_census_photons", (uint64_t)max_census);
+      d.u64("comb/rng_stream", stream);
+      comb_photons(census_photons, max_census, &rng);
+      dump_photons(d, "comb/post/", census_photons, ~size_t(0), false);
+      {
+        std::vector<uint64_t> st(census_photons.size());
+        for (size_t i = 0; i < st.size(); ++i) st[i] = census_photons[i].m_rng.data[2];
+        d.u64("comb/post/stream", st);
+      }
+      d.u64("comb/rng_draws", rng.data[0]);
     }
     d.u64("cycles_done", cycles_done);
     d.close();

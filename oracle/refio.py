@@ -48,7 +48,8 @@ def read_dump(path: str) -> dict:
 
 
 def run_reference(deck, n_ranks: int = 1, max_cycles: int | None = None, photon_limit: int | None = None,
-                  workdir: str | None = None, timeout: float = 3600.0):
+                  workdir: str | None = None, timeout: float = 3600.0, comb_max: int | None = None,
+                  comb_stream: int = 0):
     """Returns (list of per-rank dump dicts, stdout of rank 0)."""
     exe = harness_path(deck.n_groups)
     if not os.path.exists(exe):
@@ -58,6 +59,9 @@ def run_reference(deck, n_ranks: int = 1, max_cycles: int | None = None, photon_
     prefix = os.path.join(tmp, deck.name)
     env = dict(os.environ)
     env["BRANSON_SHIM_NRANKS"] = str(n_ranks)
+    if comb_max is not None:  # comb_photons on the final census (dumped under comb/...)
+        env["REF_COMB_MAX"] = str(int(comb_max))
+        env["REF_COMB_STREAM"] = str(int(comb_stream))
     args = [exe, xml, prefix, str(max_cycles if max_cycles is not None else 2 ** 31 - 1)]
     if photon_limit is not None:
         args.append(str(photon_limit))

@@ -160,6 +160,15 @@ def test_history_atomic_matches_oracle(name):
     assert worst < 1e-10
 
 
+def test_full_mesh_hohlraum_matches_oracle_photon_by_photon():
+    """The BASELINE mesh itself (65 x 65 x 140 cells, 30 groups, all 54 region blocks, reflecting and vacuum faces) at a
+    photon count the oracle finishes in half a minute: 3e5 user photons, two cycles -- the streaming first cycle
+    (~35 crossings per history) and a scattering one (~180 events per history, ~5e7 events), every per-photon integer
+    bit-exact.  (The 1e7-photon runs of tests/test_gpu_fullsize.py check the same kernel through conservation laws.)"""
+    cyc, worst = _run_cycles(decks.hohlraum_single(photons=300_000, t_stop=0.02), max_cycles=2)
+    assert cyc == 2 and worst < 1e-10
+
+
 @pytest.mark.parametrize("name", ["three_region_g30_r2", "marshak", "hohlraum_s5_g30"])
 def test_history_deterministic_matches_oracle(name):
     mk, n_ranks = CASES[name]

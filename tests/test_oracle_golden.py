@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import port
-from oracle.gen_golden import PHOTON_LIMIT, golden_cases
+from oracle.gen_golden import PHOTON_LIMIT, comb_cases, golden_cases
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -99,3 +99,22 @@ def test_oracle_reproduces_reference_bitwise(name):
 def test_golden_fixture_inventory():
     have = {os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))}
     assert have == set(golden_cases().keys())
+
+
+@pytest.mark.parametrize("name", sorted(comb_cases()))
+def test_comb_photons_matches_reference_fixture(name):
+    """orc_comb_photons against comb_photons of the unmodified reference (src/census_functions.h:48-93), run by
+    oracle/ref_harness.cc on a real census: same survivors in the same order, corrected energies bit for bit, same number
+    of RNG draws; and the comb conserves the census energy of every cell."""
+    deck, cycles, max_census, stream = comb_cases()[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cell, E = g["comb/pre/cell"], g["comb/pre/E"]
+    assert int(g["comb/max_census_photons"][0]) == max_census and int(g["comb/rng_stream"][0]) == stream
+    keep, new_E, draws = port.comb_photons(cell, E, g["comb/local_census_E"][0], max_census, deck.seed, stream)
+    assert draws == int(g["comb/rng_draws"][0]) == len(cell)
+    assert np.array_equal(g["comb/pre/stream"][keep], g["comb/post/stream"])
+    assert np.array_equal(cell[keep], g["comb/post/cell"])
+    assert np.array_equal(new_E.view(np.uint64), g["comb/post/E"].view(np.uint64))
+    before = np.bincount(cell, weights=E, minlength=int(g["n_cells"][0]))
+    after = np.bincount(cell[keep], weights=new_E, minlength=int(g["n_cells"][0]))
+    assert np.max(np.abs(before - after)) <= 1e-13 * before.max()
