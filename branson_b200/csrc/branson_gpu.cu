@@ -17,6 +17,7 @@
 
 #include "../../include/branson_gpu.h"
 #include "census.cuh"
+#include "comb.cuh"
 #include "common.cuh"
 #include "event.cuh"
 #include "mesh_dev.cuh"
@@ -60,6 +61,7 @@ struct bgpu_ctx {
 
   // photons
   PhotonSoA work{}, census{};
+  PhotonSoA comb_scratch{};  // target of the comb's compaction, swapped with `census` afterwards
   uint64_t n_work = 0, n_new = 0, n_census = 0;
   uint8_t *d_desc = nullptr;
   uint64_t desc_cap = 0;
@@ -77,7 +79,7 @@ struct bgpu_ctx {
 
   // scratch (grown on demand)
   DevBuf scr_counts, scr_offsets, scr_tile_sum, scr_tile_off, scr_tiles, scr_ndep, scr_dep_off, scr_dep_cell,
-      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event, scr_tally_rep;
+      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event, scr_tally_rep, scr_comb;
   void *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
 
@@ -754,11 +756,12 @@ void bgpu_destroy(bgpu_ctx *c) {
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->scr_counts, &c->scr_offsets, &c->scr_tile_sum, &c->scr_tile_off, &c->scr_tiles, &c->scr_ndep,
                     &c->scr_dep_off, &c->scr_dep_cell, &c->scr_dep_val, &c->scr_sort, &c->scr_keys_out,
-                    &c->scr_vals_in, &c->scr_vals_out, &c->scr_seg, &c->scr_aos, &c->scr_event, &c->scr_tally_rep};
+                    &c->scr_vals_in, &c->scr_vals_out, &c->scr_seg, &c->scr_aos, &c->scr_event, &c->scr_tally_rep,
+                    &c->scr_comb};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
-                  c->d_results, c->work.base, c->census.base, c->d_desc, c->d_counters, c->d_regions,
+                  c->d_results, c->work.base, c->census.base, c->comb_scratch.base, c->d_desc, c->d_counters, c->d_regions,
                   c->d_region_of_cell, c->d_mesh, c->d_tile_sums, c->d_mesh_sums};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -1285,6 +1288,72 @@ int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cel
   }
   CU(c, cudaMemcpyAsync(cell_tallies, c->d_tally, 16 * nc, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int bgpu_census_energy(bgpu_ctx *c, double *census_E) {
+  if (!c || !census_E) return fail(c, "bgpu_census_energy: null argument");
+  CU(c, cudaSetDevice(c->device));
+  return list_energy(c, c->census, 0, c->n_census, census_E);
+}
+
+int bgpu_comb_census(bgpu_ctx *c, uint64_t max_census_photons, double global_census_E, uint64_t rng_stream,
+                     bgpu_comb_stats *out) {
+  if (!c) return 1;
+  if (max_census_photons == 0) return fail(c, "bgpu_comb_census: max_census_photons must be positive");
+  CU(c, cudaSetDevice(c->device));
+  bgpu_comb_stats st{};
+  const uint64_t n = c->n_census;
+  st.n_before = st.n_after = n;
+  st.rng_draws = n;
+  if (list_energy(c, c->census, 0, n, &st.E_before)) return 1;
+  st.E_after = st.E_before;
+  if (!(global_census_E > 0.0)) global_census_E = st.E_before;
+  st.comb_photon_E = global_census_E / (double)(int64_t)max_census_photons;  // (:65)
+  if (n == 0) {
+    if (out) *out = st;
+    return 0;
+  }
+  const uint32_t nc = c->mesh.n_cells;
+  if (ensure(c, c->scr_dep_cell, 4 * n) || ensure(c, c->scr_vals_in, 4 * n) || ensure(c, c->scr_keys_out, 4 * n) ||
+      ensure(c, c->scr_vals_out, 4 * n) || ensure(c, c->scr_ndep, 4 * n) || ensure(c, c->scr_dep_off, 8 * (n + 1)) ||
+      ensure(c, c->scr_seg, 16ull * nc) || ensure(c, c->scr_comb, 8ull * nc))
+    return 1;
+  uint32_t *keys = (uint32_t *)c->scr_dep_cell.p, *idx = (uint32_t *)c->scr_vals_in.p;
+  uint32_t *keys_out = (uint32_t *)c->scr_keys_out.p, *order = (uint32_t *)c->scr_vals_out.p;
+  uint32_t *keep = (uint32_t *)c->scr_ndep.p;
+  uint64_t *offset = (uint64_t *)c->scr_dep_off.p;
+  uint64_t *seg_start = (uint64_t *)c->scr_seg.p, *seg_end = seg_start + nc;
+  double *new_E = (double *)c->scr_comb.p;
+  ++c->launches;
+  k_comb_draw<<<grid_for(n, 256), 256, 0, c->stream>>>(c->census.ee, c->census.sg, n, st.comb_photon_E, c->ctr_hi,
+                                                       rng_stream, keys, idx, keep);
+  int end_bit = 1;
+  while ((1ull << end_bit) < nc) ++end_bit;
+  size_t tmp_bytes = 0;
+  CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, order, (int)n, 0, end_bit, c->stream));
+  if (ensure(c, c->scr_sort, tmp_bytes)) return 1;
+  CU(c, cub::DeviceRadixSort::SortPairs(c->scr_sort.p, tmp_bytes, keys, keys_out, idx, order, (int)n, 0, end_bit,
+                                        c->stream));
+  CU(c, cudaMemsetAsync(c->scr_seg.p, 0, 16ull * nc, c->stream));
+  c->launches += 3;
+  k_seg_bounds<<<grid_for(n, 256), 256, 0, c->stream>>>(keys_out, n, seg_start, seg_end);
+  k_comb_cells<<<grid_for(nc, 128), 128, 0, c->stream>>>(nc, seg_start, seg_end, order, c->census.ee, st.comb_photon_E,
+                                                         keep, new_E);
+  CU(c, cudaGetLastError());
+  if (device_scan(c, keep, n, offset)) return 1;
+  uint64_t kept = 0;
+  CU(c, cudaMemcpyAsync(&kept, offset + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (ensure_soa(c, c->comb_scratch, kept, 0)) return 1;
+  ++c->launches;
+  k_comb_gather<<<grid_for(n, 256), 256, 0, c->stream>>>(c->census, n, keep, offset, new_E, c->comb_scratch);
+  CU(c, cudaGetLastError());
+  std::swap(c->census, c->comb_scratch);
+  c->n_census = kept;
+  st.n_after = kept;
+  if (list_energy(c, c->census, 0, kept, &st.E_after)) return 1;
+  if (out) *out = st;
   return 0;
 }
 

@@ -45,6 +45,11 @@ class CycleStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CombStats(C.Structure):
+    _fields_ = [("n_before", C.c_uint64), ("n_after", C.c_uint64), ("E_before", C.c_double), ("E_after", C.c_double),
+                ("comb_photon_E", C.c_double), ("rng_draws", C.c_uint64)]
+
+
 class PhotonSoA(C.Structure):
     _fields_ = [("n", C.c_uint64), ("cell", C.c_void_p), ("group", C.c_void_p), ("pos", C.c_void_p),
                 ("angle", C.c_void_p), ("E", C.c_void_p), ("E0", C.c_void_p), ("life_dx", C.c_void_p),
@@ -57,7 +62,7 @@ EXPORTS = [
     "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
-    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_divergence", "bgpu_set_tally_copies", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_divergence", "bgpu_census_energy", "bgpu_comb_census", "bgpu_set_tally_copies", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
     "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
     "bgpu_mesh_update_temperature", "bgpu_mesh_get",
 ]
@@ -95,6 +100,8 @@ def lib():
         L.bgpu_enable_counters.argtypes = [vp, i32]
         L.bgpu_set_launch.argtypes = [vp, i32, i32, i32]
         L.bgpu_set_divergence.argtypes = [vp, i32, i32]
+        L.bgpu_census_energy.argtypes = [vp, C.POINTER(C.c_double)]
+        L.bgpu_comb_census.argtypes = [vp, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(CombStats)]
         L.bgpu_set_tally_copies.argtypes = [vp, i32]
         L.bgpu_set_event_tail.argtypes = [vp, u64]
         L.bgpu_set_group_walk.argtypes = [vp, i32]
@@ -218,6 +225,17 @@ class Context:
 
     def set_tally_copies(self, copies=0):
         self._ck(lib().bgpu_set_tally_copies(self._h, copies))
+
+    def census_energy(self) -> float:
+        e = C.c_double()
+        self._ck(lib().bgpu_census_energy(self._h, C.byref(e)))
+        return e.value
+
+    def comb_census(self, max_census_photons: int, global_census_E: float = 0.0, rng_stream: int = 0) -> dict:
+        """comb_photons (reference src/census_functions.h:48-93) on the device census."""
+        st = CombStats()
+        self._ck(lib().bgpu_comb_census(self._h, max_census_photons, global_census_E, rng_stream, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in CombStats._fields_}
 
     def set_event_tail(self, n_active):
         self._ck(lib().bgpu_set_event_tail(self._h, n_active))

@@ -127,6 +127,24 @@ int bgpu_source(bgpu_ctx *ctx, uint32_t cycle, double dt, const double *E_emissi
  * algorithm: BGPU_HISTORY | BGPU_EVENT; tally_mode: BGPU_TALLY_ATOMIC | BGPU_TALLY_DETERMINISTIC. */
 int bgpu_transport(bgpu_ctx *ctx, double next_dt, int algorithm, int tally_mode);
 
+/* Population control of the device census: comb_photons(census_photons, max_census_photons,
+ * rng) of src/census_functions.h:48-93 -- a function the reference defines but never calls in this snapshot, so nothing
+ * here runs unless the host asks for it.  In list order each census photon takes one draw of RNG(ctx seed, rng_stream)
+ * and survives with probability E / (global_census_E / max_census_photons); a cell's last photon always survives;
+ * survivors share their cell's energy so that every cell's census energy is conserved (:86-92).  global_census_E is the
+ * census energy summed over all ranks (:61-64; bgpu_census_energy gives this rank's part; <= 0: use this rank's own).
+ * Survivors keep their list order, positions, directions and RNG state.  Same survivors and energies as the reference
+ * function on the same list (tests/test_gpu_comb.py against the oracle and the golden fixtures). */
+typedef struct {
+  uint64_t n_before, n_after; /* census size */
+  double E_before, E_after;   /* census energy (fixed-tree sums) */
+  double comb_photon_E;       /* global_census_E / max_census_photons */
+  uint64_t rng_draws;         /* = n_before: one per photon */
+} bgpu_comb_stats;
+int bgpu_census_energy(bgpu_ctx *ctx, double *census_E);
+int bgpu_comb_census(bgpu_ctx *ctx, uint64_t max_census_photons, double global_census_E, uint64_t rng_stream,
+                     bgpu_comb_stats *stats_or_null);
+
 /* rank_abs_E / rank_track_E hand-off (src/replicated_transport.h:135-140); either pointer may be NULL. */
 int bgpu_get_tallies(bgpu_ctx *ctx, double *abs_E, double *track_E, bgpu_cycle_stats *stats);
 
