@@ -61,6 +61,7 @@ bhost_driver *bhost_create(const char *xml_path, int rank, int n_ranks, const bh
       o.tally_mode = opt->tally_mode;
       o.print = opt->print != 0;
       o.mesh_on_device = opt->mesh_on_device != 0;
+      o.comb_max_census = opt->comb_max_census;
       d->driver = std::make_unique<Replicated_Driver>(*d->mesh, *d->state, *d->params, *d->comm, *d->gpu, o);
     }
   } catch (const std::exception &e) {
@@ -114,6 +115,7 @@ int bhost_cycle(bhost_driver *d, bhost_cycle_report *out) {
       o.rad_conservation = s.rad_conservation; o.mat_conservation = s.mat_conservation;
       o.rad_balance_exact = r.rad_balance_exact;
       o.trans_particles = s.g_trans_particles; o.census_size = s.g_census_size;
+      o.comb_n_before = r.comb_n_before; o.comb_n_after = r.comb_n_after;
       *out = o;
     }
   } catch (const std::exception &e) {

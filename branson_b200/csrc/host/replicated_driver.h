@@ -34,6 +34,7 @@ struct Cycle_Report {
   // wall-clock seconds of the host-visible phases of this cycle
   double t_calc_energy, t_cell_upload, t_source, t_transport, t_allreduce, t_tally_download, t_update_T, t_cycle;
   double rad_balance_exact;
+  uint64_t comb_n_before = 0, comb_n_after = 0;  // global census size around this cycle's comb (both 0: none ran)
 };
 
 struct Driver_Options {
@@ -43,6 +44,11 @@ struct Driver_Options {
   // leaves HBM and only the running sums cross PCIe.  false: the host Mesh (bit-identical to the reference's host code)
   // with f / op_a / op_s / E arrays uploaded and the tallies downloaded every cycle.
   bool mesh_on_device = false;
+  // > 0: population control -- when the global census exceeds this many photons after a cycle, comb it down to about
+  // this many (comb_photons, src/census_functions.h:48-93, whose only trace in the reference's driver is the comment
+  // of IMC_Parameters::use_comb_flag, src/imc_parameters.h:99: "Comb the census if great than n_user_photon after
+  // cycle").  0 (default): never, like the reference, whose driver does not call its comb.
+  uint64_t comb_max_census = 0;
 };
 
 inline double wall_now() {
@@ -201,9 +207,34 @@ public:
       imc_state.set_post_mat_E(0.0);
     }
     imc_state.print_conservation(comm, opt.print);
+    comb_census(rep);
     imc_state.next_time_step();
     rep.t_cycle = wall_now() - t_begin;
     return rep;
+  }
+
+  // Optional population control after a cycle (Driver_Options::comb_max_census).  Every rank combs its own census
+  // against the global census energy, as comb_photons does (src/census_functions.h:61-65); the generator is
+  // RNG(seed, 10^13 * step + 9 * 10^12 + rank): the photon streams of a step are 10^13 * step + n_user * rank + k
+  // (src/source.h:221-222), so this stream is theirs for no photon while n_user * n_ranks < 9 * 10^12.
+  void comb_census(Cycle_Report &rep) {
+    if (!opt.comb_max_census) return;
+    bgpu_ctx *ctx = gpu_setup.get_ctx();
+    uint64_t n_glob = bgpu_list_size(ctx, BGPU_LIST_CENSUS);
+    comm.sum(&n_glob, 1);
+    if (n_glob <= opt.comb_max_census) return;
+    double census_E = 0.0;
+    gpu_setup.check(bgpu_census_energy(ctx, &census_E), "bgpu_census_energy");
+    comm.sum(&census_E, 1);
+    const uint64_t stream = 10000000000000ull * imc_state.get_step() + 9000000000000ull + (uint64_t)comm.get_rank();
+    bgpu_comb_stats cs{};
+    gpu_setup.check(bgpu_comb_census(ctx, opt.comb_max_census, census_E, stream, &cs), "bgpu_comb_census");
+    uint64_t n_after = cs.n_after;
+    comm.sum(&n_after, 1);
+    rep.comb_n_before = n_glob;
+    rep.comb_n_after = n_after;
+    if (comm.get_rank() == 0 && opt.print)
+      std::cout << "census combed: " << n_glob << " -> " << n_after << " photons" << std::endl;
   }
 
   // one trip of the reference's while loop (src/replicated_driver.h:47-121)
@@ -277,6 +308,7 @@ public:
       imc_state.set_post_mat_E(0.0);
     }
     imc_state.print_conservation(comm, opt.print);
+    comb_census(rep);
     imc_state.next_time_step();
     rep.t_cycle = wall_now() - t_begin;
     return rep;

@@ -44,6 +44,8 @@ typedef struct {
   double t_stop_override;     /* <=0: keep the deck's <t_stop> */
   int32_t force_replicated;   /* 1: treat dd_transport_type as REPLICATED (the multi-node deck says PARTICLE_PASS) */
   int32_t mesh_on_device;     /* 1: calculate_photon_energy / update_temperature on the device (bgpu_mesh_*); 0: host Mesh */
+  uint64_t comb_max_census;   /* > 0: comb the census down to about this many photons whenever it exceeds that after a
+                                 cycle (bgpu_comb_census); 0: never (the reference's driver never calls its comb) */
 } bhost_options;
 
 typedef struct {
@@ -58,6 +60,7 @@ typedef struct {
    * Replicated_Driver::cycle): independent of the serial cell-order sum the reference formula uses */
   double rad_balance_exact;
   uint64_t trans_particles, census_size;
+  uint64_t comb_n_before, comb_n_after; /* global census size around this cycle's comb; both 0: no comb ran */
 } bhost_cycle_report;
 
 bhost_driver *bhost_create(const char *xml_path, int rank, int n_ranks, const bhost_options *opt,

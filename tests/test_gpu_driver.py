@@ -80,3 +80,37 @@ def test_command_line_binary_runs_a_deck(tmp_path):
     sim = port.OracleSim(deck)
     sim.cycle(keep_photons=False)
     assert f"Total Photons transported: {int(sim.get('n_photons')[0])}" in out.stdout
+
+
+@pytest.mark.parametrize("mesh_on_device", [False, True])
+def test_driver_with_census_comb_bounds_the_census_and_conserves_energy(tmp_path, mesh_on_device):
+    """Driver option comb_max_census (population control, bgpu_comb_census): on the all-reflecting cube nothing ever
+    leaves and the census settles near 40 % of the photon budget; with the comb it stays near the (three times smaller)
+    target, every cycle's radiation balance still closes to 1e-12 (the comb conserves each cell's census energy),
+    and the temperatures stay within Monte Carlo noise of the uncombed run."""
+    deck = decks.big_cube(n=16, photons=60000, t_stop=0.008)
+    xml = deck.write(str(tmp_path / "cube.xml"))
+    runs = {}
+    for target in (0, 8000):
+        d = driver.Driver(xml, n_groups=1, device=0, mesh_on_device=mesh_on_device, comb_max_census=target)
+        reps = []
+        while not d.finished():
+            reps.append(d.cycle())
+        runs[target] = (reps, d.array("T_e"))
+        d.close()
+    plain, combed = runs[0][0], runs[8000][0]
+    assert len(plain) == len(combed) == 8
+    assert all(r["comb_n_before"] == 0 for r in plain)
+    assert plain[-1]["census_size"] > 2 * 8000
+    assert sum(1 for r in combed if r["comb_n_before"] > 8000) >= 4
+    for r in combed:
+        total = r["pre_census_E"] + r["emission_E"] + r["source_E"]
+        assert abs(r["rad_balance_exact"]) <= 1e-12 * total
+        if r["comb_n_before"]:
+            assert r["comb_n_after"] < r["comb_n_before"]
+            assert 0.8 * 8000 <= r["comb_n_after"] <= 1.2 * 8000 + 16 ** 3   # ~target (+ at most one per cell)
+    # the census energy a cycle starts from is the one the previous cycle ended with, combed or not
+    for a, b in zip(combed[:-1], combed[1:]):
+        assert abs(b["pre_census_E"] - a["post_census_E"]) <= 1e-12 * a["post_census_E"]
+    T0, T1 = runs[0][1], runs[8000][1]
+    assert abs(T1.mean() - T0.mean()) <= 2e-3 * T0.mean()

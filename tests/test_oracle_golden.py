@@ -98,7 +98,7 @@ def test_oracle_reproduces_reference_bitwise(name):
 
 def test_golden_fixture_inventory():
     have = {os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))}
-    assert have == set(golden_cases().keys())
+    assert have == set(golden_cases().keys()) | set(comb_cases().keys())
 
 
 @pytest.mark.parametrize("name", sorted(comb_cases()))
