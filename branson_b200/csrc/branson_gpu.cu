@@ -549,11 +549,11 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   size_t tmp_bytes = 0;
   CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)c->scr_dep_cell.p,
                                         (uint32_t *)c->scr_keys_out.p, (const uint32_t *)c->scr_vals_in.p,
-                                        (uint32_t *)c->scr_vals_out.p, (int)n_dep, 0, end_bit, c->stream));
+                                        (uint32_t *)c->scr_vals_out.p, (uint64_t)n_dep, 0, end_bit, c->stream));
   if (ensure(c, c->scr_sort, tmp_bytes)) return 1;
   CU(c, cub::DeviceRadixSort::SortPairs(c->scr_sort.p, tmp_bytes, (const uint32_t *)c->scr_dep_cell.p,
                                         (uint32_t *)c->scr_keys_out.p, (const uint32_t *)c->scr_vals_in.p,
-                                        (uint32_t *)c->scr_vals_out.p, (int)n_dep, 0, end_bit, c->stream));
+                                        (uint32_t *)c->scr_vals_out.p, (uint64_t)n_dep, 0, end_bit, c->stream));
   if (ensure(c, c->scr_seg, 16ull * c->mesh.n_cells)) return 1;
   CU(c, cudaMemsetAsync(c->scr_seg.p, 0, 16ull * c->mesh.n_cells, c->stream));
   uint64_t *seg_start = (uint64_t *)c->scr_seg.p, *seg_end = seg_start + c->mesh.n_cells;
@@ -1314,6 +1314,7 @@ int bgpu_comb_census(bgpu_ctx *c, uint64_t max_census_photons, double global_cen
     if (out) *out = st;
     return 0;
   }
+  if (n >= (1ull << 32)) return fail(c, "bgpu_comb_census: %llu census photons (limit 2^32 - 1)", (unsigned long long)n);
   const uint32_t nc = c->mesh.n_cells;
   if (ensure(c, c->scr_dep_cell, 4 * n) || ensure(c, c->scr_vals_in, 4 * n) || ensure(c, c->scr_keys_out, 4 * n) ||
       ensure(c, c->scr_vals_out, 4 * n) || ensure(c, c->scr_ndep, 4 * n) || ensure(c, c->scr_dep_off, 8 * (n + 1)) ||
@@ -1331,9 +1332,9 @@ int bgpu_comb_census(bgpu_ctx *c, uint64_t max_census_photons, double global_cen
   int end_bit = 1;
   while ((1ull << end_bit) < nc) ++end_bit;
   size_t tmp_bytes = 0;
-  CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, order, (int)n, 0, end_bit, c->stream));
+  CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, order, (uint64_t)n, 0, end_bit, c->stream));
   if (ensure(c, c->scr_sort, tmp_bytes)) return 1;
-  CU(c, cub::DeviceRadixSort::SortPairs(c->scr_sort.p, tmp_bytes, keys, keys_out, idx, order, (int)n, 0, end_bit,
+  CU(c, cub::DeviceRadixSort::SortPairs(c->scr_sort.p, tmp_bytes, keys, keys_out, idx, order, (uint64_t)n, 0, end_bit,
                                         c->stream));
   CU(c, cudaMemsetAsync(c->scr_seg.p, 0, 16ull * nc, c->stream));
   c->launches += 3;
