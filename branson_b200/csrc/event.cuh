@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         S.c_lk = E.lk[idx];
       }
       // the parked scatter: every lane of the warp is here together (pstate_load has fetched f, sigma_a, sigma_s)
-      if (E.pending_scatter) scatter_event(S, C, __activemask());
+      if (E.pending_scatter) scatter_event<false>(S, C, __activemask());
       uint8_t descriptor = EV_PASS;
       int r = R_CONTINUE;
 #pragma unroll 1

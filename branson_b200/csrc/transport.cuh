@@ -21,6 +21,9 @@
 #include "rng.cuh"
 
 // A/B switches for tools/ timing sweeps (make variant NAME=.. EXTRA=-DBG_FM_LOG=0); the shipped build has all on
+#ifndef BG_LAZY_GROUP
+#define BG_LAZY_GROUP 1  // A/B knob: 0 = sample the group at every effective scatter (see scatter_event)
+#endif
 #ifndef BG_FM_LOG
 #define BG_FM_LOG 1
 #endif
@@ -93,6 +96,9 @@ struct PState {
   uint32_t surface;              // persists across events like the reference's surface_cross (:37)
   uint32_t c_sc, c_cr, c_rf, c_lk;  // per-photon counters: scatters, crossings, reflections, lookups
   uint32_t gmask;                // groups touched during the current cell visit (algorithmic-bytes accounting)
+  // lazily sampled group (scatter_event): cell of the history's latest effective scatter (~0u: none pending) and the low
+  // 32 bits of the counter of its group-CDF draw
+  uint32_t grp_cell, grp_ctr32;
 };
 
 struct PCtx {
@@ -152,6 +158,8 @@ __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint
   S.loc_abs = 0.0; S.loc_trk = 0.0;
   S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
+  S.grp_cell = ~0u;
+  S.grp_ctr32 = 0u;
   enter_cell(S, C);
 }
 
@@ -293,22 +301,69 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
   return r;
 }
 
-// The scatter event (:94-101).  Its draws use consecutive counters, so they are evaluated as four interleaved
-// Threefry chains: mu, phi (src/sampling_functions.h:57-70), the effective-scatter test (:98) and -- if it passes -- the
-// group CDF value (src/sampling_functions.h:126-138).  An unused fourth value is discarded, its counter not consumed.
+// sample_emission_group (src/sampling_functions.h:126-138) for the CDF draw `cdf` in cell `cell`, whose first group
+// opacity is a0 (p_grp: the cell's cached abs_groups[g] * norm when all its groups are equal, 0 = not formed yet).
+__device__ __forceinline__ int sample_group(const PCtx &C, uint32_t cell, double a0, double &p_grp, double cdf) {
+  const uint32_t G = C.G;
+  int g = -1;
+  if (C.uniform_groups && G <= 512) {
+    // All groups of the cell hold the same opacity, so every step of the reference's walk subtracts the same
+    // p = abs_groups[g] * norm and the walk stops at g = min{k : c_(k+1) <= 0}, c_(k+1) = fl(c_k - p).  The rounding
+    // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
+    // clear zero by a margin far above that bound, the sequential result is provably k0 -- no loads, no dependent
+    // chain, no divergence over the walk length.  Otherwise (probability ~1e-11 per scatter) fall through to the walk.
+    if (p_grp == 0.0) p_grp = a0 * BG_DIV(1.0, a0 * (double)G);
+    const int k0 = (int)(cdf * (double)G);
+    const double before = fma(-(double)k0, p_grp, cdf);  // c_k0 up to rounding
+    const double after = before - p_grp;                  // c_(k0+1)
+    if (before > 1.0e-13 && after < -1.0e-13 && k0 < (int)G) g = k0;
+  }
+  if (g < 0) {
+    // the sequential walk of the cell's group array, same arithmetic, loads batched by four
+    const double *ag = C.opa + (uint64_t)cell * G;
+    double a4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a4[q] = (q < (int)G) ? __ldg(&ag[q]) : 0.0;
+    const double norm = 1.0 / (a4[0] * (double)G);
+    for (uint32_t base = 0;;) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (cdf > 0.0 && base + q < G) {
+          g = (int)(base + q);
+          cdf -= a4[q] * norm;
+        }
+      }
+      base += 4;
+      if (!(cdf > 0.0) || base >= G) break;  // g == G-1 here if the walk ran off the end (round-off guard)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a4[q] = (base + q < G) ? __ldg(&ag[base + q]) : 0.0;
+    }
+  }
+  return g;
+}
+
+// The scatter event (:94-101).  Its draws sit at consecutive counters -- mu, phi (get_uniform_angle,
+// src/sampling_functions.h:57-70), the physical-vs-effective test (:98) and, if effective, the group CDF value
+// (sample_emission_group, src/sampling_functions.h:126-138) -- and are evaluated as interleaved Threefry chains.  Every
+// draw is CONSUMED exactly as in the reference (the counter is what aligns the stream); what is skipped is the
+// evaluation of draws whose value provably cannot matter:
+//   * with sigma_s == 0 the test is `u > 0`, true for every u01 value (u >= 2^-53): not evaluated when no lane of the
+//     warp has sigma_s != 0;
+//   * with one group the walk returns g = 0 for every c in (0,1): abs[0] * fl(1 / abs[0]) is 1 or 1 - 2^-53 and
+//     u01 <= 1 - 2^-53, so the first subtraction already ends the loop;
+//   * LAZY (history kernel): where all groups of every cell carry the same opacities (Cell::set_op_a fills them all,
+//     src/cell.h:260-275 -- every reference deck), the group does not enter the physics, only the photon's final
+//     record.  Only the LAST group draw of a history can be observed, so the scatter merely notes where it happened
+//     (cell, counter) and finalize_group evaluates that one draw when the history ends.
+// Every reference deck has sigma_s == 0 and faux-multigroup cells: an effective scatter then costs 2 Threefry
+// evaluations instead of 4, with bit-identical photons, counters and tallies (tests/test_gpu_parity.py: post/group).
+template <bool LAZY_OK>
 __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const unsigned lanes) {
-  // Draws of a scatter, at consecutive counters: mu, phi (get_uniform_angle), the physical-vs-effective test (:98), and
-  // -- if effective -- the group CDF value (sample_emission_group).  Two of them can be void:
-  //   * with sigma_s == 0 the test is `u > 0`, true for every u01 value (u >= 2^-53): the draw is consumed (the counter
-  //     advances) but its value cannot matter, so it is not evaluated when no lane of the warp has sigma_s != 0;
-  //   * with one group the walk returns g = 0 for every c in (0,1): abs[0] * fl(1 / abs[0]) is 1 or 1 - 2^-53, and
-  //     u01 <= 1 - 2^-53, so the first subtraction already ends the loop -- the CDF draw is consumed, not evaluated.
-  // Every reference deck has sigma_s == 0: an effective scatter then costs 3 Threefry evaluations (2 on gray decks)
-  // instead of 4, with bit-identical results and counters.
   const bool test_void = !__any_sync(lanes, S.sig_s != 0.0);
   const bool cdf_void = C.G == 1u;
+  const bool lazy = LAZY_OK && BG_LAZY_GROUP && C.uniform_groups && C.G <= 512u;
   uint64_t w_mu, w_phi, w_test = ~0ull, w_cdf = 0ull;
-  if (test_void && cdf_void) {
+  if (test_void && (cdf_void || lazy)) {
     const int off[2] = {0, 1};
     uint64_t w[2];
     threefry2x64_20_w0_multi<2>(S.ctr, C.ctr_hi, S.stream, off, w);
@@ -348,52 +403,29 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const un
     const double p_phys = (S.sig_s == 0.0) ? 0.0 : S.sig_s / ((1.0 - S.f) * S.sig_a + S.sig_s);
     if (!(u01_from_bits(w_test) > p_phys)) return;
   }
-  S.ctr += 1;
-  if (cdf_void) {  // g = 0 = the photon's group: nothing changes
-    S.gmask |= 1u;
+  S.ctr += 1;  // the group draw sits at counter S.ctr - 1
+  if (cdf_void) return;  // g = 0 = the photon's group: nothing changes
+  if (lazy) {
+    S.grp_cell = S.cell;
+    S.grp_ctr32 = (uint32_t)S.ctr - 1u;
     return;
   }
-  double cdf = u01_from_bits(w_cdf);
-  const uint32_t G = C.G;
-  int g = -1;
-  if (C.uniform_groups && G <= 512) {
-    // All groups of the cell hold the same opacity, so every step of the reference's walk subtracts the same
-    // p = abs_groups[g] * norm and the walk stops at g = min{k : c_(k+1) <= 0}, c_(k+1) = fl(c_k - p).  The rounding
-    // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
-    // clear zero by a margin far above that bound, the sequential result is provably k0 -- no loads, no dependent
-    // chain, no divergence over the walk length.  Otherwise (probability ~1e-11 per scatter) fall through to the walk.
-    if (S.p_grp == 0.0) S.p_grp = S.sig_a * BG_DIV(1.0, S.sig_a * (double)G);
-    const int k0 = (int)(cdf * (double)G);
-    const double before = fma(-(double)k0, S.p_grp, cdf);  // c_k0 up to rounding
-    const double after = before - S.p_grp;                  // c_(k0+1)
-    if (before > 1.0e-13 && after < -1.0e-13 && k0 < (int)G) g = k0;
-  }
-  if (g < 0) {
-    // sample_emission_group: sequential walk of the cell's group array, same arithmetic, loads batched by four
-    const double *ag = C.opa + (uint64_t)S.cell * G;
-    double a4[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) a4[q] = (q < (int)G) ? __ldg(&ag[q]) : 0.0;
-    const double norm = 1.0 / (a4[0] * (double)G);
-    for (uint32_t base = 0;;) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (cdf > 0.0 && base + q < G) {
-          g = (int)(base + q);
-          cdf -= a4[q] * norm;
-        }
-      }
-      base += 4;
-      if (!(cdf > 0.0) || base >= G) break;  // g == G-1 here if the walk ran off the end (round-off guard)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) a4[q] = (base + q < G) ? __ldg(&ag[base + q]) : 0.0;
-    }
-  }
+  const int g = sample_group(C, S.cell, S.sig_a, S.p_grp, u01_from_bits(w_cdf));
   if ((uint32_t)g != S.group) {
     S.group = (uint32_t)g;
     if (C.uniform_groups) S.gmask |= 1u << (S.group & 31u);  // same opacities in every group of the cell: nothing to
     else load_xs(S, C);                                        // fetch (the lookup is still counted, section 8d)
   }
+}
+
+// LAZY group sampling: the one group draw of the history that can be observed (see scatter_event).
+__device__ __forceinline__ void finalize_group(PState &S, const PCtx &C) {
+  if (S.grp_cell == ~0u) return;
+  const uint64_t ctr = S.ctr - (uint64_t)((uint32_t)S.ctr - S.grp_ctr32);  // the pending draw's counter (< 2^32 back)
+  const double cdf = u01_from_bits(threefry2x64_20_w0(ctr, C.ctr_hi, S.stream));
+  double p = 0.0;
+  S.group = (uint32_t)sample_group(C, S.grp_cell, __ldg(&C.opa[(uint64_t)S.grp_cell * C.G]), p, cdf);
+  S.grp_cell = ~0u;
 }
 
 // Per-CTA statistics of a finished history.  Shared-memory 64-bit atomics are CAS loops on sm_100a, so the counters are
@@ -496,6 +528,8 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   S.surface = 0;
   S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
   S.gmask = 0;
+  S.grp_cell = ~0u;
+  S.grp_ctr32 = 0u;
   S.p_grp = 0.0;
   LaneStats LS{0u, 0u, 0u, 0u, 0u};
   uint32_t my_idx = 0;
@@ -606,6 +640,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
         pending_scatter = true;
       } else if (r == R_DONE) {
         close_visit(S);
+        if (!RESUME) finalize_group(S, C);
         if (MODE != TM_COUNT) lane_stats_add(s_stats, LS, S);
         const uint32_t idx = my_idx;
         if (MODE == TM_COUNT) {
@@ -633,7 +668,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
       const unsigned movable = __ballot_sync(FULL, active && !pending_scatter);
       if ((uint32_t)__popc(parked) >= scatter_batch || movable == 0u) {
         if (pending_scatter) {
-          scatter_event(S, C, parked);
+          scatter_event<!RESUME>(S, C, parked);
           pending_scatter = false;
         }
       }
