@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         S.loc_abs = acc.x; S.loc_trk = acc.y;
         S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
         S.c_lk = E.lk[idx];
+        S.ev_entry = cn.x;
       }
       // the parked scatter: every lane of the warp is here together (pstate_load has fetched f, sigma_a, sigma_s)
       if (E.pending_scatter) scatter_event<false>(S, C, __activemask());
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
       for (int step = 0; step < EV_MAX_ADVANCE && r == R_CONTINUE; ++step)
         r = advance_event(S, C, bcpack, deposit, descriptor, 0u);
       if (r == R_DONE) {
-        close_visit(S);
+        close_visit(S, C, 1u);
         stats_add(s_stats, S);
         P.desc[idx] = descriptor;
         P.ph.ee[idx] = make_double2(S.E, S.E0);
@@ -114,11 +115,10 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
         if (COUNTERS)
           reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(events_of_finished(S), S.c_sc, S.c_cr, S.c_rf);
       } else {  // parked
-        close_visit(S);  // the lookup count restarts with the reload of the next pass
         P.ph.ee[idx] = make_double2(S.E, S.E0);
         pstate_store_full(S, P.ph, idx);
         E.acc[idx] = make_double2(S.loc_abs, S.loc_trk);
-        E.cnt[idx] = make_uint4(0u, S.c_sc, S.c_cr, S.c_rf);
+        E.cnt[idx] = make_uint4(S.ev_entry, S.c_sc, S.c_cr, S.c_rf);  // .x: the visit goes on in the next pass
         E.lk[idx] = S.c_lk;
         park = (r == R_SCATTER) ? 1 : 2;
       }

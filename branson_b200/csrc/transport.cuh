@@ -95,7 +95,7 @@ struct PState {
   double p_grp;                  // abs_groups[g] * norm of the current cell when all its groups are equal; 0 = not yet
   uint32_t surface;              // persists across events like the reference's surface_cross (:37)
   uint32_t c_sc, c_cr, c_rf, c_lk;  // per-photon counters: scatters, crossings, reflections, lookups
-  uint32_t gmask;                // groups touched during the current cell visit (algorithmic-bytes accounting)
+  uint32_t ev_entry;             // c_sc + c_cr + c_rf when the current cell visit began (algorithmic-bytes accounting)
   // lazily sampled group (scatter_event): cell of the history's latest effective scatter (~0u: none pending) and the low
   // 32 bits of the counter of its group-CDF draw
   uint32_t grp_cell, grp_ctr32;
@@ -131,7 +131,6 @@ __device__ __forceinline__ void load_xs(PState &S, const PCtx &C) {
   const uint64_t o = (uint64_t)S.cell * C.G + S.group;
   S.sig_a = __ldg(&C.opa[o]);
   S.sig_s = __ldg(&C.ops[o]);
-  S.gmask |= 1u << (S.group & 31u);
 }
 
 // entering a cell: Fleck factor (:58) and the opacities of the photon's group
@@ -157,7 +156,7 @@ __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint
   S.k = (int)kk; S.j = (int)jj; S.i = (int)ii;
   S.loc_abs = 0.0; S.loc_trk = 0.0;
   S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
-  S.gmask = 0;
+  S.ev_entry = 0;
   S.grp_cell = ~0u;
   S.grp_ctr32 = 0u;
   enter_cell(S, C);
@@ -171,11 +170,15 @@ __device__ __forceinline__ void pstate_store_full(const PState &S, const PhotonS
   ph.sg[idx] = make_ulonglong2(S.stream, (unsigned long long)S.cell | ((unsigned long long)S.group << 32));
 }
 
-__device__ __forceinline__ void close_visit(PState &S) {
-  // distinct (cell, group) opacity pairs touched in this visit (S_cell; group ids are hashed into
-  // 32 bits, so for G > 32 this is a lower bound)
-  S.c_lk += (uint32_t)__popc(S.gmask);
-  S.gmask = 0;
+__device__ __forceinline__ void close_visit(PState &S, const PCtx &C, const uint32_t closing_event_uncounted) {
+  // (sigma_a, sigma_s) pairs the reference algorithm fetches during this visit, SURVEY section 8d: S_cell counts one pair
+  // per event of the visit (every trip of the reference's loop re-reads its group's pair, :56-57), at most the G distinct
+  // pairs the cell has.  Counted from the event counters, not from what this kernel happens to load (with lazily
+  // sampled groups it loads one pair per visit), so that the algorithmic bytes are a property of the workload.
+  const uint32_t ev_now = S.c_sc + S.c_cr + S.c_rf;
+  const uint32_t n = ev_now - S.ev_entry + closing_event_uncounted;
+  S.c_lk += (n < C.G) ? n : C.G;
+  S.ev_entry = ev_now;
 }
 
 // The six domain boundary conditions packed three bits each (bc_type values 0..4), indexed by face: a register
@@ -290,7 +293,7 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
   }
   // (no branch taken: only reachable through NaN distances -- the reference loops as well)
   if (crossed) {  // the loads of the new cell are in flight before the tally traffic of the old one is issued
-    close_visit(S);
+    close_visit(S, C, 0u);  // (the crossing is in c_cr already)
     enter_cell(S, C);
   }
   deposit(dep, dep_cell, S.loc_abs, S.loc_trk, lanes);
@@ -303,10 +306,11 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
 
 // sample_emission_group (src/sampling_functions.h:126-138) for the CDF draw `cdf` in cell `cell`, whose first group
 // opacity is a0 (p_grp: the cell's cached abs_groups[g] * norm when all its groups are equal, 0 = not formed yet).
+template <bool CLOSED_FORM = true>
 __device__ __forceinline__ int sample_group(const PCtx &C, uint32_t cell, double a0, double &p_grp, double cdf) {
   const uint32_t G = C.G;
   int g = -1;
-  if (C.uniform_groups && G <= 512) {
+  if (CLOSED_FORM && C.uniform_groups && G <= 512) {
     // All groups of the cell hold the same opacity, so every step of the reference's walk subtracts the same
     // p = abs_groups[g] * norm and the walk stops at g = min{k : c_(k+1) <= 0}, c_(k+1) = fl(c_k - p).  The rounding
     // error accumulated over k <= G steps is below G * 2^-54, so when the residuals of the candidate k0 = floor(cdf*G)
@@ -340,6 +344,26 @@ __device__ __forceinline__ int sample_group(const PCtx &C, uint32_t cell, double
     }
   }
   return g;
+}
+
+// get_uniform_angle (src/sampling_functions.h:57-70) from the Threefry words of its two draws.
+__device__ __forceinline__ void scatter_direction(PState &S, const uint64_t w_mu, const uint64_t w_phi) {
+  const double mu = u01_from_bits(w_mu) * 2.0 - 1.0;
+  const double phi = u01_from_bits(w_phi) * 2.0 * K_PI;
+#if BG_FM_DIV
+  const double sin_theta = fm_sqrt(1.0 - mu * mu);  // mu in (-1, 1): the argument is a normal number
+#else
+  const double sin_theta = sqrt(1.0 - mu * mu);
+#endif
+  double sp, cp;
+#if BG_FM_SINCOS
+  fm_sincos(phi, &sp, &cp);
+#else
+  sincos(phi, &sp, &cp);
+#endif
+  S.ax = sin_theta * cp;
+  S.ay = sin_theta * sp;
+  S.az = mu;
 }
 
 // The scatter event (:94-101).  Its draws sit at consecutive counters -- mu, phi (get_uniform_angle,
@@ -381,22 +405,7 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const un
   }
   S.ctr += 3;
   ++S.c_sc;
-  const double mu = u01_from_bits(w_mu) * 2.0 - 1.0;
-  const double phi = u01_from_bits(w_phi) * 2.0 * K_PI;
-#if BG_FM_DIV
-  const double sin_theta = fm_sqrt(1.0 - mu * mu);  // mu in (-1, 1): the argument is a normal number
-#else
-  const double sin_theta = sqrt(1.0 - mu * mu);
-#endif
-  double sp, cp;
-#if BG_FM_SINCOS
-  fm_sincos(phi, &sp, &cp);
-#else
-  sincos(phi, &sp, &cp);
-#endif
-  S.ax = sin_theta * cp;
-  S.ay = sin_theta * sp;
-  S.az = mu;
+  scatter_direction(S, w_mu, w_phi);
   // physical vs effective scatter (src/history_based_transport.h:98-100)
   // sigma_s == 0 (every reference deck): 0 / x is exactly +0, no division needed
   if (!test_void) {
@@ -410,11 +419,11 @@ __device__ __forceinline__ void scatter_event(PState &S, const PCtx &C, const un
     S.grp_ctr32 = (uint32_t)S.ctr - 1u;
     return;
   }
-  const int g = sample_group(C, S.cell, S.sig_a, S.p_grp, u01_from_bits(w_cdf));
+  // (with LAZY_OK the closed form's cells have returned above: S.p_grp is then dead state and costs no registers)
+  const int g = sample_group<!(LAZY_OK && BG_LAZY_GROUP)>(C, S.cell, S.sig_a, S.p_grp, u01_from_bits(w_cdf));
   if ((uint32_t)g != S.group) {
     S.group = (uint32_t)g;
-    if (C.uniform_groups) S.gmask |= 1u << (S.group & 31u);  // same opacities in every group of the cell: nothing to
-    else load_xs(S, C);                                        // fetch (the lookup is still counted, section 8d)
+    if (!C.uniform_groups) load_xs(S, C);  // (same opacities in every group of the cell: nothing to fetch)
   }
 }
 
@@ -527,7 +536,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   S.f = S.sig_a = S.sig_s = S.loc_abs = S.loc_trk = 0.0;
   S.surface = 0;
   S.c_sc = S.c_cr = S.c_rf = S.c_lk = 0;
-  S.gmask = 0;
+  S.ev_entry = 0;
   S.grp_cell = ~0u;
   S.grp_ctr32 = 0u;
   S.p_grp = 0.0;
@@ -617,6 +626,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
             S.loc_abs = acc.x; S.loc_trk = acc.y;
             S.c_sc = cn.y; S.c_cr = cn.z; S.c_rf = cn.w;
             S.c_lk = P.carry_lk[idx];
+            S.ev_entry = cn.x;
             pending_scatter = P.resume_pending_scatter != 0;  // (pstate_load has fetched this visit's f, sigma_a, sigma_s)
           }
           ndep = 0;
@@ -636,11 +646,11 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
     if (go) {
       uint8_t descriptor = EV_PASS;
       const int r = advance_event(S, C, bcpack, deposit, descriptor, adv);
-      if (r == R_SCATTER) {
-        pending_scatter = true;
-      } else if (r == R_DONE) {
-        close_visit(S);
-        if (!RESUME) finalize_group(S, C);
+      if (r == R_SCATTER) pending_scatter = true;
+      if (r == R_DONE) {
+        close_visit(S, C, 1u);  // (the retiring event is in no counter, events_of_finished)
+        // (the group is observable only where the photon's record is: census photons, or everything in validation runs)
+        if (!RESUME && (P.writeback_all || descriptor == EV_CENSUS)) finalize_group(S, C);
         if (MODE != TM_COUNT) lane_stats_add(s_stats, LS, S);
         const uint32_t idx = my_idx;
         if (MODE == TM_COUNT) {

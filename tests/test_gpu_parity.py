@@ -102,6 +102,12 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
             assert st["n_scatters"] == int(sim.get("post/counters", r)[1::4].astype(np.uint64).sum())
             assert st["n_crossings"] == int(sim.get("post/counters", r)[2::4].astype(np.uint64).sum())
             assert st["n_reflections"] == int(sim.get("post/counters", r)[3::4].astype(np.uint64).sum())
+            # (sigma_a, sigma_s) pairs of the algorithmic-bytes accounting: min(G, events) per visit
+            visits = n_tot + st["n_crossings"]
+            if deck.n_groups == 1:
+                assert st["n_group_lookups"] == visits
+            else:
+                assert visits <= st["n_group_lookups"] <= min(st["n_events"], deck.n_groups * visits)
             assert st["n_killed"] == int((desc == gpu.KILLED).sum())
             assert st["n_exit"] == int((desc == gpu.EXIT).sum())
             e_scale = abs(gse)
