@@ -82,6 +82,8 @@ struct bgpu_ctx {
       scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event, scr_tally_rep, scr_comb;
   void *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
+  void *h_stage = nullptr;  // pinned staging buffers of the AoS drop-in's copy threads
+  size_t h_stage_bytes = 0;
 
   // launch config
   int block_threads = 128;
@@ -768,6 +770,7 @@ void bgpu_destroy(bgpu_ctx *c) {
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1165,24 +1168,61 @@ PhotonSoA soa_view(const PhotonSoA &s, uint64_t off) {
 // Pipelined form of the drop-in (history algorithm, atomic tallies): the photon list goes through the device in
 // slices, so that the upload of slice j+1, the transport of slice j and the download of slice j-1 overlap.  Histories
 // are independent, so slicing changes nothing per photon; all slices accumulate into the same
-// tallies.  The uploads are issued by the calling thread and the downloads by a helper thread, because copies from /
-// to pageable host memory (a std::vector) block the thread that issues them.
+// tallies.
+//
+// The caller's photons live in pageable memory (a std::vector): a plain cudaMemcpyAsync from / to it is staged by the
+// driver through one bounce buffer by the issuing thread and runs at a third of the link rate.  Here the staging is
+// ours: aos_copiers() threads per direction, each with two pinned buffers of AOS_CHUNK photons, copy between the vector
+// and their buffers (several cores' worth of memcpy bandwidth) while the DMA engines move the other buffers, so both
+// PCIe directions stay busy behind the transport kernel.
+constexpr uint64_t AOS_CHUNK = 1ull << 16;  // photons per staged copy (7.5 MB)
+constexpr int AOS_MAX_COPIERS = 8;
+constexpr int AOS_SLOTS = 2;                // pinned buffers per thread
+
+// threads per direction: BRANSON_AOS_COPIERS (1..8), default 4 or a quarter of the host's hardware threads if fewer
+int aos_copiers() {
+  int n = 4;
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (hw && (int)(hw / 4) < n) n = std::max(1, (int)(hw / 4));
+  if (const char *e = getenv("BRANSON_AOS_COPIERS")) n = atoi(e);
+  return std::min(AOS_MAX_COPIERS, std::max(1, n));
+}
+
 int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
   if (!c->s_in) {
     CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   }
-  // slices of at least 2^20 photons (enough to fill the persistent grid several times over), at most 8 of them
-  uint64_t m = std::max<uint64_t>(1ull << 20, (n + 7) / 8);
-  m = (m + 127) & ~127ull;
-  const uint32_t n_slices = (uint32_t)((n + m - 1) / m);
-  std::vector<cudaEvent_t> ev_in(n_slices), ev_done(n_slices);
-  for (uint32_t j = 0; j < n_slices; ++j) {
-    CU(c, cudaEventCreateWithFlags(&ev_in[j], cudaEventDisableTiming));
-    CU(c, cudaEventCreateWithFlags(&ev_done[j], cudaEventDisableTiming));
+  const int AOS_COPIERS = aos_copiers();
+  const size_t slot_bytes = 120 * AOS_CHUNK;
+  const size_t stage_bytes = slot_bytes * AOS_SLOTS * AOS_COPIERS * 2;
+  if (c->h_stage_bytes < stage_bytes) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_bytes = 0;
+    CU(c, cudaHostAlloc(&c->h_stage, stage_bytes, cudaHostAllocDefault));
+    c->h_stage_bytes = stage_bytes;
   }
+  // slices of at least 2^20 photons (enough to fill the persistent grid several times over), at most 8 of them, whole
+  // chunks each
+  uint64_t m = std::max<uint64_t>(1ull << 20, (n + 7) / 8);
+  m = (m + AOS_CHUNK - 1) / AOS_CHUNK * AOS_CHUNK;
+  const uint32_t n_slices = (uint32_t)((n + m - 1) / m);
+  const uint64_t chunks_per_slice = m / AOS_CHUNK;
+  const uint64_t n_chunks = (n + AOS_CHUNK - 1) / AOS_CHUNK;
+  auto chunks_of_slice = [&](uint32_t j) {
+    const uint64_t first = (uint64_t)j * chunks_per_slice;
+    return std::min<uint64_t>(chunks_per_slice, n_chunks - first);
+  };
+  std::vector<cudaEvent_t> ev_in(n_slices), ev_done(n_slices);
+  std::vector<cudaEvent_t> ev_slot((size_t)2 * AOS_COPIERS * AOS_SLOTS);
+  for (auto &e : ev_in) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : ev_done) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : ev_slot) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   auto destroy_events = [&]() {
-    for (uint32_t j = 0; j < n_slices; ++j) { cudaEventDestroy(ev_in[j]); cudaEventDestroy(ev_done[j]); }
+    for (auto &e : ev_in) cudaEventDestroy(e);
+    for (auto &e : ev_done) cudaEventDestroy(e);
+    for (auto &e : ev_slot) cudaEventDestroy(e);
   };
   uint8_t *d_aos = (uint8_t *)c->scr_aos.p;
   TransportParams P0 = make_params(c, true);
@@ -1191,28 +1231,96 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     P0.tally_rep = (double2 *)c->scr_tally_rep.p;
     P0.tally_copies = c->tally_copies_live;
   }
-  std::atomic<uint32_t> issued{0};
+  std::atomic<uint64_t> next_up{0}, next_down{0};
+  std::vector<std::atomic<uint64_t>> uploaded(n_slices);  // chunks of the slice whose H2D copy has been enqueued
+  for (auto &u : uploaded) u.store(0, std::memory_order_relaxed);
+  std::atomic<uint32_t> issued{0};  // slices whose kernels (and ev_done) have been enqueued
   std::atomic<int> abort_flag{0};
-  cudaError_t worker_err = cudaSuccess;
-  std::thread writer([&]() {
+  std::atomic<int> worker_err{(int)cudaSuccess};
+  auto fail_worker = [&](cudaError_t e) {
+    int expect = (int)cudaSuccess;
+    worker_err.compare_exchange_strong(expect, (int)e);
+    abort_flag.store(1, std::memory_order_release);
+  };
+  auto chunk_range = [&](uint64_t i, uint64_t &off, uint64_t &cnt) {
+    off = i * AOS_CHUNK;
+    cnt = std::min<uint64_t>(AOS_CHUNK, n - off);
+  };
+  // uploaders: vector -> pinned buffer -> device, chunks handed out in order
+  auto uploader = [&](int t) {
     cudaError_t e = cudaSetDevice(c->device);
-    for (uint32_t j = 0; j < n_slices && e == cudaSuccess; ++j) {
+    uint8_t *buf[AOS_SLOTS];
+    bool used[AOS_SLOTS] = {};
+    for (int k = 0; k < AOS_SLOTS; ++k) buf[k] = (uint8_t *)c->h_stage + slot_bytes * (size_t)(t * AOS_SLOTS + k);
+    for (int turn = 0; e == cudaSuccess; ++turn) {
+      if (abort_flag.load(std::memory_order_acquire)) return;
+      const uint64_t i = next_up.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n_chunks) break;
+      const int k = turn % AOS_SLOTS;
+      cudaEvent_t ev = ev_slot[t * AOS_SLOTS + k];
+      if (used[k]) e = cudaEventSynchronize(ev);  // the buffer's previous copy has left it
+      if (e != cudaSuccess) break;
+      uint64_t off, cnt;
+      chunk_range(i, off, cnt);
+      memcpy(buf[k], photons + 120 * off, 120 * cnt);
+      e = cudaMemcpyAsync(d_aos + 120 * off, buf[k], 120 * cnt, cudaMemcpyHostToDevice, c->s_in);
+      if (e == cudaSuccess) e = cudaEventRecord(ev, c->s_in);
+      used[k] = true;
+      if (e == cudaSuccess) uploaded[i / chunks_per_slice].fetch_add(1, std::memory_order_release);
+    }
+    if (e != cudaSuccess) fail_worker(e);
+  };
+  // downloaders: device -> pinned buffer -> vector, once the chunk's slice has been transported
+  auto downloader = [&](int t) {
+    cudaError_t e = cudaSetDevice(c->device);
+    uint8_t *buf[AOS_SLOTS];
+    for (int k = 0; k < AOS_SLOTS; ++k)
+      buf[k] = (uint8_t *)c->h_stage + slot_bytes * (size_t)((AOS_COPIERS + t) * AOS_SLOTS + k);
+    uint64_t pend_off[AOS_SLOTS], pend_cnt[AOS_SLOTS];
+    bool pending[AOS_SLOTS] = {};
+    auto drain = [&](int k) {
+      if (!pending[k] || e != cudaSuccess) return;
+      e = cudaEventSynchronize(ev_slot[(AOS_COPIERS + t) * AOS_SLOTS + k]);
+      if (e == cudaSuccess) memcpy(photons + 120 * pend_off[k], buf[k], 120 * pend_cnt[k]);
+      pending[k] = false;
+    };
+    for (int turn = 0; e == cudaSuccess; ++turn) {
+      const uint64_t i = next_down.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n_chunks) break;
+      const uint32_t j = (uint32_t)(i / chunks_per_slice);
       while (issued.load(std::memory_order_acquire) <= j) {
         if (abort_flag.load(std::memory_order_acquire)) return;
         std::this_thread::yield();
       }
-      const uint64_t off = (uint64_t)j * m, cnt = std::min<uint64_t>(m, n - off);
-      e = cudaEventSynchronize(ev_done[j]);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(photons + 120 * off, d_aos + 120 * off, 120 * cnt, cudaMemcpyDeviceToHost, c->s_out);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_out);
+      const int k = turn % AOS_SLOTS;
+      drain(k);
+      if (e != cudaSuccess) break;
+      chunk_range(i, pend_off[k], pend_cnt[k]);
+      cudaEvent_t ev = ev_slot[(AOS_COPIERS + t) * AOS_SLOTS + k];
+      // (s_out is FIFO: one wait on the slice's event orders every copy queued behind it)
+      e = cudaStreamWaitEvent(c->s_out, ev_done[j], 0);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(buf[k], d_aos + 120 * pend_off[k], 120 * pend_cnt[k], cudaMemcpyDeviceToHost, c->s_out);
+      if (e == cudaSuccess) e = cudaEventRecord(ev, c->s_out);
+      pending[k] = e == cudaSuccess;
     }
-    worker_err = e;
-  });
+    for (int k = 0; k < AOS_SLOTS; ++k) drain(k);
+    if (e != cudaSuccess) fail_worker(e);
+  };
+  std::vector<std::thread> threads;
+  for (int t = 0; t < AOS_COPIERS; ++t) threads.emplace_back(uploader, t);
+  for (int t = 0; t < AOS_COPIERS; ++t) threads.emplace_back(downloader, t);
+
   cudaError_t e = cudaSuccess;
   for (uint32_t j = 0; j < n_slices && e == cudaSuccess; ++j) {
     const uint64_t off = (uint64_t)j * m, cnt = std::min<uint64_t>(m, n - off);
-    e = cudaMemcpyAsync(d_aos + 120 * off, photons + 120 * off, 120 * cnt, cudaMemcpyHostToDevice, c->s_in);
-    if (e == cudaSuccess) e = cudaEventRecord(ev_in[j], c->s_in);
+    while (uploaded[j].load(std::memory_order_acquire) < chunks_of_slice(j)) {
+      if (abort_flag.load(std::memory_order_acquire)) break;
+      std::this_thread::yield();
+    }
+    if (abort_flag.load(std::memory_order_acquire)) break;
+    // every H2D copy of the slice is in s_in's queue by now: an event recorded behind them covers them all
+    e = cudaEventRecord(ev_in[j], c->s_in);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, ev_in[j], 0);
     if (e != cudaSuccess) break;
     const PhotonSoA view = soa_view(c->work, off);
@@ -1232,16 +1340,19 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     if (e == cudaSuccess) issued.store(j + 1, std::memory_order_release);
   }
   if (e != cudaSuccess) abort_flag.store(1, std::memory_order_release);
-  writer.join();
-  if (e == cudaSuccess && c->tally_copies_live > 1) {
+  for (auto &th : threads) th.join();
+  if (e == cudaSuccess && !abort_flag.load() && c->tally_copies_live > 1) {
     ++c->launches;
     k_fold_tally<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>((double2 *)c->d_tally, P0.tally_rep,
                                                                           c->mesh.n_cells, c->tally_copies_live - 1);
     e = cudaGetLastError();
   }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_in);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_out);
   destroy_events();
   if (e != cudaSuccess) return fail(c, "bgpu_transport_photons_aos: %s", cudaGetErrorString(e));
-  if (worker_err != cudaSuccess) return fail(c, "bgpu_transport_photons_aos (download): %s", cudaGetErrorString(worker_err));
+  if (worker_err.load() != (int)cudaSuccess)
+    return fail(c, "bgpu_transport_photons_aos (copy thread): %s", cudaGetErrorString((cudaError_t)worker_err.load()));
   return 0;
 }
 
