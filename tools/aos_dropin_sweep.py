@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--copiers", default="1,2,4,6,8")
 ap.add_argument("--photons", type=int, default=bench.PHOTONS_PER_GPU)
 args = ap.parse_args()
-deck = bench.make_deck(1, 3, args.photons)
+deck = bench.make_deck(1, 8, args.photons)  # the run must not be over when the drop-in is timed
 xml = deck.write(os.path.join(tempfile.mkdtemp(prefix="aos_"), "deck.xml"))
 d = driver.Driver(xml, n_groups=bench.N_GROUPS, device=0, mesh_on_device=False)
 for _ in range(3):
