@@ -1469,6 +1469,34 @@ int bgpu_comb_census(bgpu_ctx *c, uint64_t max_census_photons, double global_cen
   return 0;
 }
 
+int bgpu_sort_census_by_cell(bgpu_ctx *c) {
+  if (!c) return 1;
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t n = c->n_census;
+  if (n < 2) return 0;
+  if (n >= (1ull << 32)) return fail(c, "bgpu_sort_census_by_cell: %llu census photons (limit 2^32 - 1)", (unsigned long long)n);
+  if (ensure(c, c->scr_dep_cell, 4 * n) || ensure(c, c->scr_vals_in, 4 * n) || ensure(c, c->scr_keys_out, 4 * n) ||
+      ensure(c, c->scr_vals_out, 4 * n))
+    return 1;
+  uint32_t *keys = (uint32_t *)c->scr_dep_cell.p, *idx = (uint32_t *)c->scr_vals_in.p;
+  uint32_t *keys_out = (uint32_t *)c->scr_keys_out.p, *order = (uint32_t *)c->scr_vals_out.p;
+  ++c->launches;
+  k_cell_keys<<<grid_for(n, 256), 256, 0, c->stream>>>(c->census.sg, n, keys, idx);
+  int end_bit = 1;
+  while ((1ull << end_bit) < c->mesh.n_cells) ++end_bit;
+  size_t tmp_bytes = 0;
+  CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, order, (uint64_t)n, 0, end_bit, c->stream));
+  if (ensure(c, c->scr_sort, tmp_bytes)) return 1;
+  CU(c, cub::DeviceRadixSort::SortPairs(c->scr_sort.p, tmp_bytes, keys, keys_out, idx, order, (uint64_t)n, 0, end_bit,
+                                        c->stream));
+  if (ensure_soa(c, c->comb_scratch, n, 0)) return 1;
+  c->launches += 2;
+  k_permute_soa<<<grid_for(n, 256), 256, 0, c->stream>>>(c->census, n, order, c->comb_scratch);
+  CU(c, cudaGetLastError());
+  std::swap(c->census, c->comb_scratch);
+  return 0;
+}
+
 uint64_t bgpu_list_size(const bgpu_ctx *c, int which) {
   if (!c) return 0;
   return which == BGPU_LIST_CENSUS ? c->n_census : c->n_work;

@@ -270,4 +270,26 @@ __global__ void __launch_bounds__(CT_THREADS) k_scan_apply(const uint32_t *__res
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == CT_THREADS - 1) out[n] = tile_off[gridDim.x];
 }
 
+// Census ordered by cell: sort key and identity permutation ...
+__global__ void k_cell_keys(const ulonglong2 *__restrict__ sg, uint64_t n, uint32_t *__restrict__ key,
+                            uint32_t *__restrict__ index) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = (uint32_t)sg[i].y;
+  index[i] = (uint32_t)i;
+}
+
+// ... and dst[o] = src[order[o]]: gathered 16-byte loads, coalesced stores.
+__global__ void k_permute_soa(PhotonSoA src, uint64_t n, const uint32_t *__restrict__ order, PhotonSoA dst) {
+  const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const uint32_t i = order[o];
+  dst.xy[o] = src.xy[i];
+  dst.za[o] = src.za[i];
+  dst.bc[o] = src.bc[i];
+  dst.ee[o] = src.ee[i];
+  dst.lc[o] = src.lc[i];
+  dst.sg[o] = src.sg[i];
+}
+
 }  // namespace bg

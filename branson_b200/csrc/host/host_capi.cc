@@ -62,6 +62,7 @@ bhost_driver *bhost_create(const char *xml_path, int rank, int n_ranks, const bh
       o.print = opt->print != 0;
       o.mesh_on_device = opt->mesh_on_device != 0;
       o.comb_max_census = opt->comb_max_census;
+      o.sort_census = opt->sort_census != 0;
       d->driver = std::make_unique<Replicated_Driver>(*d->mesh, *d->state, *d->params, *d->comm, *d->gpu, o);
     }
   } catch (const std::exception &e) {

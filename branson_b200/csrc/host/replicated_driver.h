@@ -49,6 +49,9 @@ struct Driver_Options {
   // of IMC_Parameters::use_comb_flag, src/imc_parameters.h:99: "Comb the census if great than n_user_photon after
   // cycle").  0 (default): never, like the reference, whose driver does not call its comb.
   uint64_t comb_max_census = 0;
+  // true: the census is sorted by cell after every cycle (bgpu_sort_census_by_cell): memory
+  // locality for the next cycle's transport; no per-photon result changes.  false (default): the reference's order.
+  bool sort_census = false;
 };
 
 inline double wall_now() {
@@ -218,6 +221,11 @@ public:
   // RNG(seed, 10^13 * step + 9 * 10^12 + rank): the photon streams of a step are 10^13 * step + n_user * rank + k
   // (src/source.h:221-222), so this stream is theirs for no photon while n_user * n_ranks < 9 * 10^12.
   void comb_census(Cycle_Report &rep) {
+    comb_if_over(rep);
+    // Optional locality ordering of what is left (Driver_Options::sort_census)
+    if (opt.sort_census) gpu_setup.check(bgpu_sort_census_by_cell(gpu_setup.get_ctx()), "bgpu_sort_census_by_cell");
+  }
+  void comb_if_over(Cycle_Report &rep) {
     if (!opt.comb_max_census) return;
     bgpu_ctx *ctx = gpu_setup.get_ctx();
     uint64_t n_glob = bgpu_list_size(ctx, BGPU_LIST_CENSUS);

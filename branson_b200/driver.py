@@ -35,7 +35,7 @@ class Options(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("device", C.c_int32), ("tally_mode", C.c_int32), ("algorithm", C.c_int32),
                 ("print", C.c_int32), ("validate", C.c_int32), ("no_gpu", C.c_int32),
                 ("photons_override", C.c_uint64), ("t_stop_override", C.c_double), ("force_replicated", C.c_int32),
-                ("mesh_on_device", C.c_int32), ("comb_max_census", C.c_uint64)]
+                ("mesh_on_device", C.c_int32), ("comb_max_census", C.c_uint64), ("sort_census", C.c_int32)]
 
 
 class CycleReport(C.Structure):
@@ -173,11 +173,11 @@ class Driver:
 
     def __init__(self, xml_path, n_groups=1, rank=0, n_ranks=1, device=-1, tally_mode=gpu.TALLY_ATOMIC, algorithm=-1,
                  print_report=False, validate=False, no_gpu=False, photons=0, t_stop=0.0, force_replicated=False,
-                 comm: TorchComm | None = None, mesh_on_device=False, comb_max_census=0):
+                 comm: TorchComm | None = None, mesh_on_device=False, comb_max_census=0, sort_census=False):
         L = lib()
         o = Options(n_groups, device, tally_mode, algorithm, 1 if print_report else 0, 1 if validate else 0,
                     1 if no_gpu else 0, photons, t_stop, 1 if force_replicated else 0, 1 if mesh_on_device else 0,
-                    int(comb_max_census))
+                    int(comb_max_census), 1 if sort_census else 0)
         err = C.create_string_buffer(1024)
         self._comm = comm
         self._h = L.bhost_create(str(xml_path).encode(), rank, n_ranks, C.byref(o),

@@ -62,7 +62,7 @@ EXPORTS = [
     "bgpu_device_count", "bgpu_last_error", "bgpu_create", "bgpu_destroy", "bgpu_set_cell_data",
     "bgpu_set_cell_groups", "bgpu_source", "bgpu_transport", "bgpu_get_tallies", "bgpu_tally_buffer", "bgpu_sync",
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
-    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_divergence", "bgpu_census_energy", "bgpu_comb_census", "bgpu_set_tally_copies", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
+    "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_divergence", "bgpu_census_energy", "bgpu_comb_census", "bgpu_sort_census_by_cell", "bgpu_set_tally_copies", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
     "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
     "bgpu_mesh_update_temperature", "bgpu_mesh_get",
 ]
@@ -102,6 +102,7 @@ def lib():
         L.bgpu_set_divergence.argtypes = [vp, i32, i32]
         L.bgpu_census_energy.argtypes = [vp, C.POINTER(C.c_double)]
         L.bgpu_comb_census.argtypes = [vp, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(CombStats)]
+        L.bgpu_sort_census_by_cell.argtypes = [vp]
         L.bgpu_set_tally_copies.argtypes = [vp, i32]
         L.bgpu_set_event_tail.argtypes = [vp, u64]
         L.bgpu_set_group_walk.argtypes = [vp, i32]
@@ -230,6 +231,10 @@ class Context:
         e = C.c_double()
         self._ck(lib().bgpu_census_energy(self._h, C.byref(e)))
         return e.value
+
+    def sort_census_by_cell(self) -> None:
+        """bgpu_sort_census_by_cell: stable sort of the device census by cell."""
+        self._ck(lib().bgpu_sort_census_by_cell(self._h))
 
     def comb_census(self, max_census_photons: int, global_census_E: float = 0.0, rng_stream: int = 0) -> dict:
         """comb_photons (reference src/census_functions.h:48-93) on the device census."""

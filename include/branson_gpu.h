@@ -145,6 +145,14 @@ int bgpu_census_energy(bgpu_ctx *ctx, double *census_E);
 int bgpu_comb_census(bgpu_ctx *ctx, uint64_t max_census_photons, double global_census_E, uint64_t rng_stream,
                      bgpu_comb_stats *stats_or_null);
 
+/* Locality-aware photon order between cycles: stable sort of the device census by cell, so
+ * that neighbouring lanes of the next cycle's transport work in neighbouring cells (cell data and tally lines shared,
+ * more same-cell deposits for the warp aggregation).  The reference keeps the census in the order post_process_photons
+ * appended it (src/post_process_functions.h:33-59); a photon's history depends on nothing but its own state (SURVEY
+ * section 8a, N5), so the order changes no per-photon result -- only the order in which tallies are summed (and with
+ * it the meaning of "the reference's serial order" in BGPU_TALLY_DETERMINISTIC).  Off unless the host asks for it. */
+int bgpu_sort_census_by_cell(bgpu_ctx *ctx);
+
 /* rank_abs_E / rank_track_E hand-off (src/replicated_transport.h:135-140); either pointer may be NULL. */
 int bgpu_get_tallies(bgpu_ctx *ctx, double *abs_E, double *track_E, bgpu_cycle_stats *stats);
 

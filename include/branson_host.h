@@ -46,6 +46,8 @@ typedef struct {
   int32_t mesh_on_device;     /* 1: calculate_photon_energy / update_temperature on the device (bgpu_mesh_*); 0: host Mesh */
   uint64_t comb_max_census;   /* > 0: comb the census down to about this many photons whenever it exceeds that after a
                                  cycle (bgpu_comb_census); 0: never (the reference's driver never calls its comb) */
+  int32_t sort_census;        /* 1: sort the census by cell after every cycle (bgpu_sort_census_by_cell); 0: keep the
+                                 reference's order */
 } bhost_options;
 
 typedef struct {
