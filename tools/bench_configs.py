@@ -118,10 +118,11 @@ def main_multi(a, algo):
     dist.destroy_process_group()
 
 
-def run_case(name, deck, cycles, algorithm):
+def run_case(name, deck, cycles, algorithm, sort_census=False):
     tmp = tempfile.mkdtemp(prefix="bcfg_")
     xml = deck.write(os.path.join(tmp, f"{name}.xml"))
-    d = driver.Driver(xml, n_groups=deck.n_groups, device=0, algorithm=algorithm, mesh_on_device=True)
+    d = driver.Driver(xml, n_groups=deck.n_groups, device=0, algorithm=algorithm, mesh_on_device=True,
+                      sort_census=sort_census)
     peak, peak_src = bench.measured_peak()
     rows = []
     for c in range(cycles):
@@ -153,6 +154,7 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--scale-photons", type=float, default=1.0)
     ap.add_argument("--algorithm", default="history", choices=["history", "event"])
+    ap.add_argument("--sort-census", action="store_true", help="driver option sort_census (census ordered by cell)")
     ap.add_argument("--multi", action="store_true", help="the multi-GPU decks, one rank per GPU (run under torchrun)")
     a = ap.parse_args()
     algo = gpu.EVENT if a.algorithm == "event" else gpu.HISTORY
@@ -162,7 +164,7 @@ def main():
     for name, (deck, cycles) in cases(a.scale_photons).items():
         if a.only and name not in a.only.split(","):
             continue
-        res = run_case(name, deck, cycles, algo)
+        res = run_case(name, deck, cycles, algo, a.sort_census)
         out.append(res)
         print(f"== {name}  (G={deck.n_groups}, photons={deck.photons:.3g})")
         print("  cyc   transported     ms    Mhist/s  ev/h  sc/h  cr/h   B/hist   GB/s  hbm%  Gdraw/s")
