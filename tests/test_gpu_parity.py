@@ -32,6 +32,9 @@ def _close(got, want, scale=None, what=""):
     return float(err.max() / s) if s > 0 else 0.0
 
 
+_LOOKUPS = {}
+
+
 def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATOMIC, max_cycles=None, launch=None,
                 event_tail=None, closed_form_walk=True, group_arrays=False, tuning=None):
     sim = port.OracleSim(deck, n_ranks=n_ranks)
@@ -108,6 +111,10 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
                 assert st["n_group_lookups"] == visits
             else:
                 assert visits <= st["n_group_lookups"] <= min(st["n_events"], deck.n_groups * visits)
+            # ... and a property of the workload: the same for every algorithm / tally mode / launch geometry that has
+            # transported this deck in this session
+            seen = _LOOKUPS.setdefault((deck.name, deck.n_groups, deck.photons, n_ranks, cyc, r), st["n_group_lookups"])
+            assert st["n_group_lookups"] == seen
             assert st["n_killed"] == int((desc == gpu.KILLED).sum())
             assert st["n_exit"] == int((desc == gpu.EXIT).sum())
             e_scale = abs(gse)
