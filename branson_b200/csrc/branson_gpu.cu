@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -37,11 +38,14 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int WORK_COUNTERS = 16;  // [0]: every ordinary launch; [j]: slice j of the pipelined AoS drop-in
+
 struct bgpu_ctx {
   int device = 0;
   int n_sm = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined AoS drop-in (created on first use)
+  cudaStream_t s_k2 = nullptr;                   // its second compute stream
   cudaEvent_t ev[6] = {};
   std::string err;
 
@@ -342,7 +346,8 @@ int device_scan(bgpu_ctx *c, const uint32_t *in, uint64_t n, uint64_t *out) {
 }
 
 template <int MODE, bool RESUME = false>
-int launch_history(bgpu_ctx *c, const TransportParams &P) {
+int launch_history(bgpu_ctx *c, const TransportParams &P, cudaStream_t stream = nullptr) {
+  if (!stream) stream = c->stream;
   const size_t smem = (size_t)P.mesh.n_faces * 8;
   const bool use_smem = smem <= 160 * 1024;
   const bool ctrs = P.counters != nullptr;
@@ -360,7 +365,7 @@ int launch_history(bgpu_ctx *c, const TransportParams &P) {
   const uint64_t max_useful = (P.n + c->block_threads - 1) / c->block_threads;
   if (blocks > max_useful) blocks = std::max<uint64_t>(max_useful, 1);
   ++c->launches;
-  kern<<<(unsigned)blocks, c->block_threads, use_smem ? smem : 0, c->stream>>>(P);
+  kern<<<(unsigned)blocks, c->block_threads, use_smem ? smem : 0, stream>>>(P);
   CU(c, cudaGetLastError());
   return 0;
 }
@@ -456,6 +461,17 @@ int prepare_tally_copies(bgpu_ctx *c) {
   return 0;
 }
 
+// photons a warp takes from the work list at a time
+uint32_t chunk_for(const bgpu_ctx *c, uint64_t n) {
+  if (!c->chunk_auto) return c->chunk;
+  // at least ~8 chunks per resident warp, so the last chunks do not leave most of the machine idle (marshak /
+  // hot_zone: 1e6 photons over 2960 warps)
+  const uint64_t warps = (uint64_t)c->n_sm * 5 * 4;
+  uint64_t ch = n / (warps * 8);
+  ch = std::max<uint64_t>(32, std::min<uint64_t>(c->chunk, ch & ~31ull));
+  return (uint32_t)ch;
+}
+
 TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   TransportParams P{};
   P.ph = c->work;
@@ -469,15 +485,7 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   P.tally = (double2 *)c->d_tally;
   P.ctr_hi = c->ctr_hi;
   P.work_counter = c->d_work_counter;
-  P.chunk = c->chunk;
-  if (c->chunk_auto) {
-    // at least ~8 chunks per resident warp, so the last chunks do not leave most of the machine idle (marshak /
-    // hot_zone: 1e6 photons over 2960 warps)
-    const uint64_t warps = (uint64_t)c->n_sm * 5 * 4;
-    uint64_t ch = c->n_work / (warps * 8);
-    ch = std::max<uint64_t>(32, std::min<uint64_t>(c->chunk, ch & ~31ull));
-    P.chunk = (uint32_t)ch;
-  }
+  P.chunk = chunk_for(c, c->n_work);
   P.inv_sxy = 1.0 / ((double)c->mesh.nx * (double)c->mesh.ny);
   P.inv_nx = 1.0 / (double)c->mesh.nx;
   P.scatter_batch = c->scatter_batch;
@@ -733,7 +741,7 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   CUC(cudaMemset(c->d_tally, 0, 16 * nc));
   CUC(cudaMalloc((void **)&c->d_stats, 8 * ST_COUNT));
   CUC(cudaMemset(c->d_stats, 0, 8 * ST_COUNT));
-  CUC(cudaMalloc((void **)&c->d_work_counter, 8));
+  CUC(cudaMalloc((void **)&c->d_work_counter, 8 * WORK_COUNTERS));
   CUC(cudaMalloc((void **)&c->d_results, 8 * 8));
   uint64_t cap = d->photon_capacity;
   if (!cap) cap = (uint64_t)(1.25 * (double)d->n_user_photons / (double)c->n_ranks) + 1024;
@@ -772,6 +780,7 @@ void bgpu_destroy(bgpu_ctx *c) {
     if (ev) cudaEventDestroy(ev);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_k2) cudaStreamDestroy(c->s_k2);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1179,11 +1188,13 @@ constexpr uint64_t AOS_CHUNK = 1ull << 16;  // photons per staged copy (7.5 MB)
 constexpr int AOS_MAX_COPIERS = 8;
 constexpr int AOS_SLOTS = 2;                // pinned buffers per thread
 
-// threads per direction: BRANSON_AOS_COPIERS (1..8), default 4 or a quarter of the host's hardware threads if fewer
+// threads per direction: BRANSON_AOS_COPIERS (1..8); default 6, or 3/8 of the host's hardware threads if that is fewer
+// (both directions together then use 3/4 of them).  Measured on a 16-thread host: 2 -> 118 ms, 4 -> 87 ms, 6 -> 79 ms,
+// 8 -> no better (tools/aos_dropin_sweep.py; the copies are then bound by the host's memory bandwidth).
 int aos_copiers() {
-  int n = 4;
+  int n = 6;
   const unsigned hw = std::thread::hardware_concurrency();
-  if (hw && (int)(hw / 4) < n) n = std::max(1, (int)(hw / 4));
+  if (hw && (int)(hw * 3 / 8) < n) n = std::max(1, (int)(hw * 3 / 8));
   if (const char *e = getenv("BRANSON_AOS_COPIERS")) n = atoi(e);
   return std::min(AOS_MAX_COPIERS, std::max(1, n));
 }
@@ -1192,6 +1203,7 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
   if (!c->s_in) {
     CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->s_k2, cudaStreamNonBlocking));
   }
   const int AOS_COPIERS = aos_copiers();
   const size_t slot_bytes = 120 * AOS_CHUNK;
@@ -1203,9 +1215,9 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     CU(c, cudaHostAlloc(&c->h_stage, stage_bytes, cudaHostAllocDefault));
     c->h_stage_bytes = stage_bytes;
   }
-  // slices of at least 2^20 photons (enough to fill the persistent grid several times over), at most 8 of them, whole
-  // chunks each
-  uint64_t m = std::max<uint64_t>(1ull << 20, (n + 7) / 8);
+  // slices of at least 2^19 photons (enough to fill the persistent grid several times over), at most WORK_COUNTERS of
+  // them, whole chunks each
+  uint64_t m = std::max<uint64_t>(1ull << 19, (n + WORK_COUNTERS - 1) / WORK_COUNTERS);
   m = (m + AOS_CHUNK - 1) / AOS_CHUNK * AOS_CHUNK;
   const uint32_t n_slices = (uint32_t)((n + m - 1) / m);
   const uint64_t chunks_per_slice = m / AOS_CHUNK;
@@ -1219,7 +1231,10 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
   for (auto &e : ev_in) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : ev_done) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : ev_slot) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaEvent_t ev_ready;
+  CU(c, cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
   auto destroy_events = [&]() {
+    cudaEventDestroy(ev_ready);
     for (auto &e : ev_in) cudaEventDestroy(e);
     for (auto &e : ev_done) cudaEventDestroy(e);
     for (auto &e : ev_slot) cudaEventDestroy(e);
@@ -1307,13 +1322,23 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     for (int k = 0; k < AOS_SLOTS; ++k) drain(k);
     if (e != cudaSuccess) fail_worker(e);
   };
+  const bool trace = getenv("BRANSON_AOS_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  double t_issued_all = 0.0;
+  // The slices run on two compute streams in turn, each slice with its own work counter: a slice's photons come from one
+  // part of the list (new photons are in cell order), so their histories are alike and its persistent grid drains
+  // unevenly -- the next slice's CTAs take over the SMs as they fall idle.  (One stream: 94 ms of kernel time for the
+  // 69 ms the unsliced list takes under the same profiler.)
+  cudaError_t e = cudaSuccess;
+  e = cudaEventRecord(ev_ready, c->stream);  // tallies uploaded, statistics and tally copies zeroed
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_k2, ev_ready, 0);
   std::vector<std::thread> threads;
   for (int t = 0; t < AOS_COPIERS; ++t) threads.emplace_back(uploader, t);
   for (int t = 0; t < AOS_COPIERS; ++t) threads.emplace_back(downloader, t);
-
-  cudaError_t e = cudaSuccess;
   for (uint32_t j = 0; j < n_slices && e == cudaSuccess; ++j) {
     const uint64_t off = (uint64_t)j * m, cnt = std::min<uint64_t>(m, n - off);
+    cudaStream_t sk = (j & 1u) ? c->s_k2 : c->stream;
     while (uploaded[j].load(std::memory_order_acquire) < chunks_of_slice(j)) {
       if (abort_flag.load(std::memory_order_acquire)) break;
       std::this_thread::yield();
@@ -1321,25 +1346,44 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     if (abort_flag.load(std::memory_order_acquire)) break;
     // every H2D copy of the slice is in s_in's queue by now: an event recorded behind them covers them all
     e = cudaEventRecord(ev_in[j], c->s_in);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, ev_in[j], 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ev_in[j], 0);
     if (e != cudaSuccess) break;
     const PhotonSoA view = soa_view(c->work, off);
     c->launches += 2;  // + the history kernel, counted by launch_history
-    k_aos_to_soa<<<grid_for(cnt, 128), 128, 0, c->stream>>>((const uint64_t *)(d_aos + 120 * off), cnt, view, c->ctr_hi,
-                                                            c->d_stats);
+    k_aos_to_soa<<<grid_for(cnt, 128), 128, 0, sk>>>((const uint64_t *)(d_aos + 120 * off), cnt, view, c->ctr_hi,
+                                                     c->d_stats);
     TransportParams P = P0;
     P.ph = view;
     P.n = cnt;
     P.desc = c->d_desc + off;
     if (P.counters) P.counters += 4 * off;
-    e = cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream);
-    if (e == cudaSuccess && launch_history<TM_ATOMIC>(c, P)) e = cudaErrorUnknown;
-    k_soa_to_aos<<<grid_for(cnt, 128), 128, 0, c->stream>>>((uint64_t *)(d_aos + 120 * off), cnt, view, c->d_desc + off);
+    P.work_counter = c->d_work_counter + j;
+    P.chunk = chunk_for(c, cnt);
+    e = cudaMemsetAsync(P.work_counter, 0, 8, sk);
+    if (e == cudaSuccess && launch_history<TM_ATOMIC>(c, P, sk)) e = cudaErrorUnknown;
+    k_soa_to_aos<<<grid_for(cnt, 128), 128, 0, sk>>>((uint64_t *)(d_aos + 120 * off), cnt, view, c->d_desc + off);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaEventRecord(ev_done[j], c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_done[j], sk);
     if (e == cudaSuccess) issued.store(j + 1, std::memory_order_release);
   }
+  // the caller's stream goes on (tally fold, tally download) once the other compute stream has finished its slices
+  if (e == cudaSuccess && n_slices > 1) {
+    const uint32_t last_odd = (n_slices - 1) | 1u;
+    e = cudaStreamWaitEvent(c->stream, ev_done[last_odd < n_slices ? last_odd : last_odd - 2], 0);
+  }
   if (e != cudaSuccess) abort_flag.store(1, std::memory_order_release);
+  t_issued_all = ms_since();
+  if (trace) {
+    cudaStreamSynchronize(c->s_in);
+    const double t_up = ms_since();
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->s_k2);
+    const double t_k = ms_since();
+    for (auto &th : threads) th.join();
+    fprintf(stderr, "[aos] %u slices, %d copiers: last slice issued %.1f ms, uploads done %.1f, kernels done %.1f, downloads done %.1f\n",
+            n_slices, AOS_COPIERS, t_issued_all, t_up, t_k, ms_since());
+    threads.clear();
+  }
   for (auto &th : threads) th.join();
   if (e == cudaSuccess && !abort_flag.load() && c->tally_copies_live > 1) {
     ++c->launches;
