@@ -223,13 +223,15 @@ __global__ void k_expand_groups(uint32_t n_cells, uint32_t G, const double *__re
   ops[t] = s[cell];
 }
 
+// cells whose groups do not all carry the same (sigma_a, sigma_s) pair: with none of them the photon's group never enters
+// the physics (closed-form group walk, no reload on a group change, lazily sampled groups: transport.cuh)
 __global__ void k_count_nonuniform_cells(uint32_t n_cells, uint32_t G, const double *__restrict__ opa,
-                                         unsigned long long *count) {
+                                         const double *__restrict__ ops, unsigned long long *count) {
   const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= n_cells) return;
-  const double *a = opa + (uint64_t)cell * G;
+  const double *a = opa + (uint64_t)cell * G, *sc = ops + (uint64_t)cell * G;
   bool same = true;
-  for (uint32_t g = 1; g < G; ++g) same = same && (a[g] == a[0]);
+  for (uint32_t g = 1; g < G; ++g) same = same && (a[g] == a[0]) && (sc[g] == sc[0]);
   if (!same) atomicAdd(count, 1ull);
 }
 
@@ -812,7 +814,8 @@ int bgpu_set_cell_groups(bgpu_ctx *c, const double *f, const double *abs_groups,
   CU(c, cudaMemcpyAsync(c->d_ops, sct_groups, 8 * nc * G, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemsetAsync(c->d_stats, 0, 8 * ST_COUNT, c->stream));
   ++c->launches;
-  k_count_nonuniform_cells<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_opa, c->d_stats);
+  k_count_nonuniform_cells<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_opa, c->d_ops,
+                                                                    c->d_stats);
   unsigned long long nonuniform = 0;
   CU(c, cudaMemcpyAsync(&nonuniform, c->d_stats, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));

@@ -298,3 +298,35 @@ def test_empty_and_no_cell_data_errors():
     a, t, st = ctx.tallies()
     assert not a.any() and not t.any() and st["n_census"] == 0 and st["census_E"] == 0.0
     ctx.close()
+
+
+def test_group_dependent_scattering_is_not_treated_as_gray():
+    """Cells whose groups share sigma_a but not sigma_s are genuinely multigroup: the photon's group enters the physics
+    through the physical-vs-effective test, so none of the uniform-group shortcuts (closed-form walk, no reload on a
+    group change, lazily sampled groups) may apply.  The event-based variant never takes those shortcuts: HISTORY must
+    give the same photons, and the group dependence must be visible against the gray run."""
+    deck = decks.simple_three_region(photons=20000, n_groups=30)
+    sim = port.OracleSim(deck)
+    sim.cycle(keep_photons=False)
+    G = deck.n_groups
+    f, op_a, op_s = sim.get("f"), sim.get("op_a"), sim.get("op_s")
+    abs_groups = np.repeat(op_a, G)
+    sct_gray = np.repeat(op_s, G)
+    sct_groups = sct_gray * np.tile(1.0 + (np.arange(G) % 3), deck.n_cells)
+    out = {}
+    for key, algorithm, sct in (("history", gpu.HISTORY, sct_groups), ("event", gpu.EVENT, sct_groups),
+                                ("gray", gpu.HISTORY, sct_gray)):
+        ctx = gpu.context_for_deck(deck, sim.get("mesh/nodes"), device=0)
+        ctx.enable_counters(True)
+        ctx.set_cell_groups(f, abs_groups, sct)
+        ctx.source(1, sim.get("dt")[0], sim.get("E_emission"), sim.get("E_source"), sim.get("E_census"),
+                   sim.get("global_source_energy")[0])
+        ctx.transport(sim.get("next_dt")[0], algorithm, gpu.TALLY_ATOMIC)
+        out[key] = (ctx.download(gpu.LIST_WORK, counters=True), ctx.tallies())
+        ctx.close()
+    h, e, g = out["history"][0], out["event"][0], out["gray"][0]
+    for k in ("cell", "group", "ctr", "descriptor", "counters"):
+        assert np.array_equal(h[k], e[k]), k
+    assert np.array_equal(h["E"].view(np.uint64), e["E"].view(np.uint64))
+    assert out["history"][1][2]["n_group_lookups"] == out["event"][1][2]["n_group_lookups"]
+    assert not np.array_equal(h["ctr"], g["ctr"])  # the test has power: group-dependent sigma_s changes the histories
