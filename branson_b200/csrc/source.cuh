@@ -12,6 +12,7 @@
 //                       get_initial_census_photon (:117-131) pos (3) -> angle (2) -> group, life_dx = c*dt.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 #include "rng.cuh"
 
 namespace bg {
@@ -54,8 +55,9 @@ struct SourceParams {
   double dt;
 };
 
-// The (at most seven) draws of one new photon use the consecutive counters 0..7 of its own stream: they are evaluated
-// up front as two batches of four interleaved Threefry chains (rng.cuh) and handed out in the reference's draw order.
+// The (at most seven) draws of one new photon use the consecutive counters 0..6 of its own stream: they are evaluated
+// up front as a batch of four and a batch of three interleaved Threefry chains (rng.cuh; w[7] is never handed out) and
+// handed out in the reference's draw order.
 struct Draws {
   uint64_t w[8];
   uint32_t used;
@@ -73,9 +75,10 @@ __device__ __forceinline__ void uniform_angle(Draws &D, double &ax, double &ay, 
   // src/sampling_functions.h:57-70
   const double mu = D.next() * 2.0 - 1.0;
   const double phi = D.next() * 2.0 * K_PI;
-  const double sin_theta = sqrt(1.0 - mu * mu);
+  // the same routines as the scatter of the history loop (transport.cuh scatter_direction): mu in (-1, 1), phi in [0, 2 pi)
+  const double sin_theta = fm_sqrt(1.0 - mu * mu);
   double sp, cp;
-  sincos(phi, &sp, &cp);
+  fm_sincos(phi, &sp, &cp);
   ax = sin_theta * cp;
   ay = sin_theta * sp;
   az = mu;
@@ -122,7 +125,12 @@ __global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
   const uint64_t stream = P.stream_base + k;
   Draws D;
   threefry2x64_20_w0_x4(0, P.ctr_hi, stream, D.w);
-  threefry2x64_20_w0_x4(4, P.ctr_hi, stream, D.w + 4);
+  {
+    const int off[3] = {4, 5, 6};
+    uint64_t v[3];
+    threefry2x64_20_w0_multi<3>(0, P.ctr_hi, stream, off, v);
+    D.w[4] = v[0]; D.w[5] = v[1]; D.w[6] = v[2]; D.w[7] = 0;
+  }
   D.used = 0;
   double x, y, z, ax, ay, az, life;
   if (!boundary_source) {
