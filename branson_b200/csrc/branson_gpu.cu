@@ -58,6 +58,7 @@ struct bgpu_ctx {
 
   // cell data
   double *d_f = nullptr, *d_opa = nullptr, *d_ops = nullptr;  // f [n_cells]; opa/ops [n_cells*G]
+  double *d_cellrec = nullptr;  // {f, sigma_a, sigma_s, 0} per cell (32 B): what a visit needs where groups are uniform
   double *d_cell_stage = nullptr;                               // 3*n_cells staging (gray values / E arrays)
   bool have_cell_data = false;
   bool closed_form_walk = true;
@@ -235,6 +236,17 @@ __global__ void k_count_nonuniform_cells(uint32_t n_cells, uint32_t G, const dou
   if (!same) atomicAdd(count, 1ull);
 }
 
+// One 32-byte record per cell for decks whose groups all carry the same opacities: a cell visit then costs one sector
+// instead of three (f, abs_groups[g], sct_groups[g] live in three arrays, the latter two 8 G bytes per cell), and the
+// whole table (19 MB for the hohlraum's 591 500 cells, against 289 MB) stays in L2 next to the tallies.
+__global__ void k_fill_cellrec(uint32_t n_cells, uint32_t G, const double *__restrict__ f, const double *__restrict__ opa,
+                               const double *__restrict__ ops, double *__restrict__ rec) {
+  const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  reinterpret_cast<double2 *>(rec)[2 * (uint64_t)cell] = make_double2(f[cell], opa[(uint64_t)cell * G]);
+  reinterpret_cast<double2 *>(rec)[2 * (uint64_t)cell + 1] = make_double2(ops[(uint64_t)cell * G], 0.0);
+}
+
 __global__ void k_copy_soa(PhotonSoA src, uint64_t src_off, PhotonSoA dst, uint64_t dst_off, uint64_t n) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -353,9 +365,17 @@ int launch_history(bgpu_ctx *c, const TransportParams &P, cudaStream_t stream = 
   const size_t smem = (size_t)P.mesh.n_faces * 8;
   const bool use_smem = smem <= 160 * 1024;
   const bool ctrs = P.counters != nullptr;
+  // PACKED: the cell's record instead of the three cell-data arrays (transport.cuh enter_cell); the RESUME launches of the
+  // event variant keep the arrays (they share event.cuh's device functions)
+  const bool packed = !RESUME && P.uniform_groups != 0;
   void (*kern)(const TransportParams) = nullptr;
-  if (use_smem) kern = ctrs ? k_transport_history<MODE, true, true, RESUME> : k_transport_history<MODE, false, true, RESUME>;
-  else kern = ctrs ? k_transport_history<MODE, true, false, RESUME> : k_transport_history<MODE, false, false, RESUME>;
+  if (packed) {
+    if (use_smem) kern = ctrs ? k_transport_history<MODE, true, true, false, true> : k_transport_history<MODE, false, true, false, true>;
+    else kern = ctrs ? k_transport_history<MODE, true, false, false, true> : k_transport_history<MODE, false, false, false, true>;
+  } else {
+    if (use_smem) kern = ctrs ? k_transport_history<MODE, true, true, RESUME, false> : k_transport_history<MODE, false, true, RESUME, false>;
+    else kern = ctrs ? k_transport_history<MODE, true, false, RESUME, false> : k_transport_history<MODE, false, false, RESUME, false>;
+  }
   if (use_smem && smem > 48 * 1024)
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = c->blocks_per_sm;
@@ -484,6 +504,7 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   P.f = c->d_f;
   P.opa = c->d_opa;
   P.ops = c->d_ops;
+  P.cellrec = reinterpret_cast<const double2 *>(c->d_cellrec);
   P.tally = (double2 *)c->d_tally;
   P.ctr_hi = c->ctr_hi;
   P.work_counter = c->d_work_counter;
@@ -738,6 +759,7 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   CUC(cudaMalloc((void **)&c->d_f, 8 * nc));
   CUC(cudaMalloc((void **)&c->d_opa, 8 * nc * G));
   CUC(cudaMalloc((void **)&c->d_ops, 8 * nc * G));
+  CUC(cudaMalloc((void **)&c->d_cellrec, 32 * nc));
   CUC(cudaMalloc((void **)&c->d_cell_stage, 8 * nc * 3));
   CUC(cudaMalloc((void **)&c->d_tally, 16 * nc));
   CUC(cudaMemset(c->d_tally, 0, 16 * nc));
@@ -772,7 +794,7 @@ void bgpu_destroy(bgpu_ctx *c) {
                     &c->scr_comb};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
-  void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
+  void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cellrec, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
                   c->d_results, c->work.base, c->census.base, c->comb_scratch.base, c->d_desc, c->d_counters, c->d_regions,
                   c->d_region_of_cell, c->d_mesh, c->d_tile_sums, c->d_mesh_sums};
   for (void *p : ptrs)
@@ -798,6 +820,9 @@ int bgpu_set_cell_data(bgpu_ctx *c, const double *f, const double *op_a, const d
   ++c->launches;
   k_expand_groups<<<grid_for(nc * c->mesh.G, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_cell_stage,
                                                                         c->d_cell_stage + nc, c->d_opa, c->d_ops);
+  ++c->launches;
+  k_fill_cellrec<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_f, c->d_opa, c->d_ops,
+                                                          c->d_cellrec);
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));  // the host arrays may be rewritten as soon as we return
   c->have_cell_data = true;
@@ -816,6 +841,9 @@ int bgpu_set_cell_groups(bgpu_ctx *c, const double *f, const double *abs_groups,
   ++c->launches;
   k_count_nonuniform_cells<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_opa, c->d_ops,
                                                                     c->d_stats);
+  ++c->launches;
+  k_fill_cellrec<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_f, c->d_opa, c->d_ops,
+                                                          c->d_cellrec);  // (only read if the groups turn out uniform)
   unsigned long long nonuniform = 0;
   CU(c, cudaMemcpyAsync(&nonuniform, c->d_stats, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -1024,6 +1052,9 @@ int bgpu_mesh_calculate_photon_energy(bgpu_ctx *c, double dt, uint32_t step, bgp
   ++c->launches;
   k_expand_groups<<<grid_for((uint64_t)c->mesh.n_cells * c->mesh.G, 256), 256, 0, c->stream>>>(
       c->mesh.n_cells, c->mesh.G, P.op_a, P.op_s, c->d_opa, c->d_ops);
+  ++c->launches;
+  k_fill_cellrec<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_f, c->d_opa,
+                                                                        c->d_ops, c->d_cellrec);
   CU(c, cudaGetLastError());
   c->have_cell_data = true;
   c->uniform_groups = true;

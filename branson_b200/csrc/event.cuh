@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, 4) k_event_pass(const EventParams E) {
   C.fz = C.fy + (P.mesh.ny + 1);
   C.nx = P.mesh.nx; C.ny = P.mesh.ny; C.nz = P.mesh.nz; C.G = P.mesh.G;
   C.sxy = C.nx * C.ny;
-  C.f = P.f; C.opa = P.opa; C.ops = P.ops;
+  C.f = P.f; C.opa = P.opa; C.ops = P.ops; C.cellrec = P.cellrec;
   C.ctr_hi = P.ctr_hi;
   C.uniform_groups = P.uniform_groups != 0;
   C.inv_sxy = P.inv_sxy; C.inv_nx = P.inv_nx;

@@ -55,6 +55,7 @@ struct TransportParams {
   const double *f;    // [n_cells]
   const double *opa;  // [n_cells][G]
   const double *ops;  // [n_cells][G]
+  const double2 *cellrec;  // [n_cells][2]: {f, sigma_a}, {sigma_s, 0} -- valid where uniform_groups
   double2 *tally;     // [n_cells] {abs_E, track_E}
   uint64_t ctr_hi;    // seed << 32
   unsigned long long *work_counter;
@@ -105,6 +106,7 @@ struct PCtx {
   const double *fx, *fy, *fz;    // per-axis faces (shared memory when they fit)
   uint32_t nx, ny, nz, G, sxy;
   const double *f, *opa, *ops;
+  const double2 *cellrec;        // packed per-cell records (k_fill_cellrec), read by the PACKED instantiations
   uint64_t ctr_hi;
   bool uniform_groups;
   double inv_sxy, inv_nx;
@@ -134,12 +136,25 @@ __device__ __forceinline__ void load_xs(PState &S, const PCtx &C) {
 }
 
 // entering a cell: Fleck factor (:58) and the opacities of the photon's group
+// PACKED (history kernel on decks whose cells carry the same opacities in every group, P.uniform_groups): the visit's
+// three values come from the cell's 32-byte record {f, sigma_a, sigma_s, 0} (k_fill_cellrec) -- one address, one sector,
+// and a table that stays in L2 (19 MB for the hohlraum's 591 500 cells; the [cell][G] arrays are 289 MB, and a photon
+// entering a cell found their three sectors evicted: 9.2 GB of DRAM reads per hohlraum launch)
+template <bool PACKED = false>
 __device__ __forceinline__ void enter_cell(PState &S, const PCtx &C) {
-  S.f = __ldg(&C.f[S.cell]);
   S.p_grp = 0.0;
-  load_xs(S, C);
+  if (PACKED) {
+    const double2 *r = C.cellrec + 2 * (uint64_t)S.cell;
+    const double2 fa = __ldg(r);
+    S.sig_s = __ldg(reinterpret_cast<const double *>(r + 1));
+    S.f = fa.x; S.sig_a = fa.y;
+  } else {
+    S.f = __ldg(&C.f[S.cell]);
+    load_xs(S, C);
+  }
 }
 
+template <bool PACKED = false>
 __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint64_t idx, const PCtx &C) {
   const double2 xy = ph.xy[idx], za = ph.za[idx], bc = ph.bc[idx], ee = ph.ee[idx];
   const ulonglong2 lc = ph.lc[idx], sg = ph.sg[idx];
@@ -159,7 +174,7 @@ __device__ __forceinline__ void pstate_load(PState &S, const PhotonSoA &ph, uint
   S.ev_entry = 0;
   S.grp_cell = ~0u;
   S.grp_ctr32 = 0u;
-  enter_cell(S, C);
+  enter_cell<PACKED>(S, C);
 }
 
 __device__ __forceinline__ void pstate_store_full(const PState &S, const PhotonSoA &ph, uint64_t idx) {
@@ -198,7 +213,7 @@ __host__ __device__ __forceinline__ uint32_t pack_bc(const int *bc) {
 // path six times per trip at 4 of 32 lanes -- and every deposit of the trip (cell left, photon killed / escaped /
 // reaching census) is issued from ONE converged site: deposit(do_it, cell, abs, trk, lanes), called by every lane of
 // `lanes` (the lanes that entered this function together), which lets the caller combine same-cell deposits.
-template <class Deposit>
+template <bool PACKED = false, class Deposit>
 __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uint32_t bcpack, Deposit &&deposit,
                                              uint8_t &descriptor, const unsigned lanes) {
   const double total_sigma_s = (1.0 - S.f) * S.sig_a + S.sig_s;
@@ -294,7 +309,7 @@ __device__ __forceinline__ int advance_event(PState &S, const PCtx &C, const uin
   // (no branch taken: only reachable through NaN distances -- the reference loops as well)
   if (crossed) {  // the loads of the new cell are in flight before the tally traffic of the old one is issued
     close_visit(S, C, 0u);  // (the crossing is in c_cr already)
-    enter_cell(S, C);
+    enter_cell<PACKED>(S, C);
   }
   deposit(dep, dep_cell, S.loc_abs, S.loc_trk, lanes);
   if (dep) {
@@ -493,7 +508,7 @@ __device__ __forceinline__ void stats_flush(const uint32_t *s_stats, unsigned lo
 
 // RESUME: the launch continues histories that the event-based passes (event.cuh) parked at a pending scatter: photon
 // indices come from P.index_list, the thread-local tallies and counters from P.carry_*.
-template <int MODE, bool COUNTERS, bool SMEM, bool RESUME>
+template <int MODE, bool COUNTERS, bool SMEM, bool RESUME, bool PACKED>
 __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const TransportParams P) {
   extern __shared__ double s_faces[];
   __shared__ uint32_t s_stats[12];
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
   C.fz = C.fy + (P.mesh.ny + 1);
   C.nx = P.mesh.nx; C.ny = P.mesh.ny; C.nz = P.mesh.nz; C.G = P.mesh.G;
   C.sxy = C.nx * C.ny;
-  C.f = P.f; C.opa = P.opa; C.ops = P.ops;
+  C.f = P.f; C.opa = P.opa; C.ops = P.ops; C.cellrec = P.cellrec;
   // the counter's high word is seed << 32 (src/RNG.h:318-330): rebuilt from its upper half so that the compiler knows the
   // low 32 bits are zero and folds them out of the first Threefry round
   C.ctr_hi = (uint64_t)(uint32_t)(P.ctr_hi >> 32) << 32;
@@ -618,7 +633,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
         if (!active && r < avail) {
           const uint32_t slot = q_next + r;
           const uint32_t idx = RESUME ? P.index_list[slot] : slot;
-          pstate_load(S, P.ph, idx, C);
+          pstate_load<PACKED>(S, P.ph, idx, C);
           my_idx = idx;
           if (RESUME) {
             const double2 acc = P.carry_acc[idx];
@@ -645,7 +660,7 @@ __global__ void __launch_bounds__(128, BG_MIN_BLOCKS) k_transport_history(const 
     const unsigned adv = __ballot_sync(FULL, go);
     if (go) {
       uint8_t descriptor = EV_PASS;
-      const int r = advance_event(S, C, bcpack, deposit, descriptor, adv);
+      const int r = advance_event<PACKED>(S, C, bcpack, deposit, descriptor, adv);
       if (r == R_SCATTER) pending_scatter = true;
       if (r == R_DONE) {
         close_visit(S, C, 1u);  // (the retiring event is in no counter, events_of_finished)
