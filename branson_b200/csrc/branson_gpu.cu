@@ -96,7 +96,7 @@ struct bgpu_ctx {
   uint32_t chunk = 128;
   bool chunk_auto = true;      // shrink the chunk when the work list is too short to give every warp several
   uint32_t scatter_batch = 12;  // history kernel: parked scatters a warp waits for before sampling them together
-  int aggregate = 1;            // history kernel: combine same-cell deposits of a warp trip
+  int aggregate = -1;           // history kernel: combine same-cell deposits of a warp trip (-1: by mesh size)
   int tally_copies = 0;         // replicated tallies of the history kernel (0: auto from the mesh size, 1: off)
   uint32_t tally_copies_live = 0;  // copies the zeroed scr_tally_rep currently holds (+1 for the main tally)
   uint64_t event_tail = 0;   // active-list size below which BGPU_EVENT hands over to the history kernel (0: auto)
@@ -469,9 +469,17 @@ int run_event(bgpu_ctx *c, TransportParams P) {
 // Replicated tallies (transport.cuh, TransportParams::tally_rep): as many copies as fit 64 MB (L2-sized), at most 64;
 // big meshes (8e6 cells) get none -- their deposits are spread over so many addresses that nothing serialises.  The
 // copies are zero between launches (k_fold_tally re-zeroes them).
+// Tally-contention measures (warp-aggregated deposits, replicated tallies) pay where many photons deposit into few
+// cells -- marshak's 25 cells, hot_zone's 5 x 5 hot corner of 40 000 -- and cost where they do not: on the 591 500-cell
+// hohlraum and the 8e6-cell cube the same-cell matching finds nothing to combine (hohlraum streaming cycle +9 %,
+// multi-node share +12 %, big_cube +7 %, hohlraum scattering cycles +2 % without them; profiles/sweep_r01_v15.txt).
+// Unless the host says otherwise (bgpu_set_divergence, bgpu_set_tally_copies) they are on for meshes below 2^17 cells.
+bool contended_mesh(const bgpu_ctx *c) { return c->mesh.n_cells < (1u << 17); }
+
 int prepare_tally_copies(bgpu_ctx *c) {
   uint32_t copies = c->tally_copies > 0 ? (uint32_t)c->tally_copies
-                                        : (uint32_t)std::min<uint64_t>(64, (64ull << 20) / (16ull * c->mesh.n_cells));
+                    : !contended_mesh(c) ? 1u
+                                         : (uint32_t)std::min<uint64_t>(64, (64ull << 20) / (16ull * c->mesh.n_cells));
   if (copies < 1) copies = 1;
   if (c->tally_copies_live == copies) return 0;
   if (copies > 1) {
@@ -512,7 +520,7 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   P.inv_sxy = 1.0 / ((double)c->mesh.nx * (double)c->mesh.ny);
   P.inv_nx = 1.0 / (double)c->mesh.nx;
   P.scatter_batch = c->scatter_batch;
-  P.aggregate = c->aggregate;
+  P.aggregate = c->aggregate >= 0 ? c->aggregate : (contended_mesh(c) ? 1 : 0);
   P.writeback_all = writeback_all ? 1 : 0;
   P.stats = c->d_stats;
   P.uniform_groups = (c->uniform_groups && c->closed_form_walk) ? 1 : 0;
@@ -1602,7 +1610,7 @@ int bgpu_set_divergence(bgpu_ctx *c, int scatter_batch, int aggregate_deposits) 
   if (!c) return 1;
   if (scatter_batch > 32) return fail(c, "bgpu_set_divergence: scatter_batch is a lane count (1..32, 0 = keep)");
   if (scatter_batch > 0) c->scatter_batch = (uint32_t)scatter_batch;
-  if (aggregate_deposits >= 0) c->aggregate = aggregate_deposits ? 1 : 0;
+  if (aggregate_deposits >= 0) c->aggregate = aggregate_deposits ? 1 : 0;  // (< 0 keeps: by mesh size unless set before)
   return 0;
 }
 

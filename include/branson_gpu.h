@@ -186,11 +186,12 @@ int bgpu_set_launch(bgpu_ctx *ctx, int block_threads, int blocks_per_sm, int chu
 /* History kernel, divergence and tally-contention control (per-photon results do not depend on either; only the
  * summation order of the atomic tallies does): scatter_batch = lanes of a warp that must be parked at a scatter before
  * the warp samples them together (1 = sample immediately, 0 = keep the current value, default 12); aggregate_deposits =
- * 1 (default) combines the same-cell deposits of a warp trip into one pair of atomics, 0 issues them per lane, < 0 keeps. */
+ * 1 combines the same-cell deposits of a warp trip into one pair of atomics, 0 issues them per lane, < 0 keeps the
+ * current setting (default: on for meshes below 2^17 cells, where photons crowd into few cells, off above). */
 int bgpu_set_divergence(bgpu_ctx *ctx, int scatter_batch, int aggregate_deposits);
 /* Replicated tallies of the history kernel (atomic mode): warps deposit into `copies` separate tally arrays that are
  * summed into the tally buffer after the launch, which divides the same-address reduction traffic of hot cells.
- * 0 = auto (as many as fit 64 MB, at most 64), 1 = off. */
+ * 0 = auto (meshes below 2^17 cells: as many as fit 64 MB, at most 64; larger meshes: off), 1 = off. */
 int bgpu_set_tally_copies(bgpu_ctx *ctx, int copies);
 /* BGPU_EVENT: active-list size at or below which the lockstep passes hand the remaining histories to the persistent
  * history kernel (0 = auto: twice the number of resident lanes) */
