@@ -93,7 +93,7 @@ struct bgpu_ctx {
   // launch config
   int block_threads = 128;
   int blocks_per_sm = 0;  // 0: occupancy query
-  uint32_t chunk = 128;
+  uint32_t chunk = 64;   // (v16 sweep: 64 is 0.5 % ahead of 128 on the hohlraum, 256 is 3 % behind; profiles/sweep_r01_v15.txt)
   bool chunk_auto = true;      // shrink the chunk when the work list is too short to give every warp several
   uint32_t scatter_batch = 12;  // history kernel: parked scatters a warp waits for before sampling them together
   int aggregate = -1;           // history kernel: combine same-cell deposits of a warp trip (-1: by mesh size)
