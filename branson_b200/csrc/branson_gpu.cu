@@ -96,6 +96,8 @@ struct bgpu_ctx {
   uint32_t chunk = 64;   // (v16 sweep: 64 is 0.5 % ahead of 128 on the hohlraum, 256 is 3 % behind; profiles/sweep_r01_v15.txt)
   bool chunk_auto = true;      // shrink the chunk when the work list is too short to give every warp several
   uint32_t scatter_batch = 12;  // history kernel: parked scatters a warp waits for before sampling them together
+  bool scatter_batch_auto = true;   // ... 6 instead, when the previous launch's histories were short (make_params)
+  double prev_events_per_history = 0.0;  // of the previous transport launch (0: none yet)
   int aggregate = -1;           // history kernel: combine same-cell deposits of a warp trip (-1: by mesh size)
   int tally_copies = 0;         // replicated tallies of the history kernel (0: auto from the mesh size, 1: off)
   uint32_t tally_copies_live = 0;  // copies the zeroed scr_tally_rep currently holds (+1 for the main tally)
@@ -520,6 +522,10 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   P.inv_sxy = 1.0 / ((double)c->mesh.nx * (double)c->mesh.ny);
   P.inv_nx = 1.0 / (double)c->mesh.nx;
   P.scatter_batch = c->scatter_batch;
+  // In a history of a handful of events a lane parked at a scatter idles for a large part of it while the warp collects
+  // twelve: the short-history multi-node hohlraum (4.8 events per history) runs 3.5 % faster at 4-8, the decks with
+  // 30+ events per history want 8-16 (profiles/sweep_r01_v15.txt).  The previous cycle's event count decides.
+  if (c->scatter_batch_auto && c->prev_events_per_history > 0.0 && c->prev_events_per_history < 16.0) P.scatter_batch = 6;
   P.aggregate = c->aggregate >= 0 ? c->aggregate : (contended_mesh(c) ? 1 : 0);
   P.writeback_all = writeback_all ? 1 : 0;
   P.stats = c->d_stats;
@@ -675,6 +681,7 @@ int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
   s.n_deposits = st[ST_DEPOSITS];
   s.n_group_lookups = st[ST_LOOKUPS];
   s.n_launches = c->launches;
+  if (s.n_transported) c->prev_events_per_history = (double)s.n_events / (double)s.n_transported;
   return 0;
 }
 
@@ -741,7 +748,7 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   CUC(cudaGetDeviceProperties(&prop, dev));
   c->n_sm = prop.multiProcessorCount;
   // tuning sweeps (tools/): BGPU_SCATTER_BATCH, BGPU_AGGREGATE, BGPU_CHUNK override the defaults of a new context
-  if (const char *e = getenv("BGPU_SCATTER_BATCH")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->scatter_batch = (uint32_t)v; }
+  if (const char *e = getenv("BGPU_SCATTER_BATCH")) { const int v = atoi(e); if (v >= 1 && v <= 32) { c->scatter_batch = (uint32_t)v; c->scatter_batch_auto = false; } }
   if (const char *e = getenv("BGPU_AGGREGATE")) c->aggregate = atoi(e) ? 1 : 0;
   if (const char *e = getenv("BGPU_TALLY_COPIES")) { const int v = atoi(e); if (v >= 0 && v <= 1024) c->tally_copies = v; }
   if (const char *e = getenv("BGPU_CHUNK")) { const int v = atoi(e); if (v > 0) { c->chunk = (uint32_t)v; c->chunk_auto = false; } }
@@ -1609,7 +1616,7 @@ int bgpu_set_launch(bgpu_ctx *c, int block_threads, int blocks_per_sm, int chunk
 int bgpu_set_divergence(bgpu_ctx *c, int scatter_batch, int aggregate_deposits) {
   if (!c) return 1;
   if (scatter_batch > 32) return fail(c, "bgpu_set_divergence: scatter_batch is a lane count (1..32, 0 = keep)");
-  if (scatter_batch > 0) c->scatter_batch = (uint32_t)scatter_batch;
+  if (scatter_batch > 0) { c->scatter_batch = (uint32_t)scatter_batch; c->scatter_batch_auto = false; }
   if (aggregate_deposits >= 0) c->aggregate = aggregate_deposits ? 1 : 0;  // (< 0 keeps: by mesh size unless set before)
   return 0;
 }

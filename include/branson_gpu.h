@@ -185,7 +185,8 @@ int bgpu_enable_counters(bgpu_ctx *ctx, int on);
 int bgpu_set_launch(bgpu_ctx *ctx, int block_threads, int blocks_per_sm, int chunk_photons);
 /* History kernel, divergence and tally-contention control (per-photon results do not depend on either; only the
  * summation order of the atomic tallies does): scatter_batch = lanes of a warp that must be parked at a scatter before
- * the warp samples them together (1 = sample immediately, 0 = keep the current value, default 12); aggregate_deposits =
+ * the warp samples them together (1 = sample immediately, 0 = keep the current value; default 12, or 6 when the previous
+ * launch's histories averaged fewer than 16 events); aggregate_deposits =
  * 1 combines the same-cell deposits of a warp trip into one pair of atomics, 0 issues them per lane, < 0 keeps the
  * current setting (default: on for meshes below 2^17 cells, where photons crowd into few cells, off above). */
 int bgpu_set_divergence(bgpu_ctx *ctx, int scatter_batch, int aggregate_deposits);
