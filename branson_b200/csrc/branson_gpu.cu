@@ -98,7 +98,7 @@ struct bgpu_ctx {
   uint32_t scatter_batch = 12;  // history kernel: parked scatters a warp waits for before sampling them together
   bool scatter_batch_auto = true;   // ... 6 instead, when the previous launch's histories were short (make_params)
   double prev_events_per_history = 0.0;  // of the previous transport launch (0: none yet)
-  int aggregate = -1;           // history kernel: combine same-cell deposits of a warp trip (-1: by mesh size)
+  int aggregate = 0;            // history kernel: combine same-cell deposits of a warp trip (off: see contended_mesh)
   int tally_copies = 0;         // replicated tallies of the history kernel (0: auto from the mesh size, 1: off)
   uint32_t tally_copies_live = 0;  // copies the zeroed scr_tally_rep currently holds (+1 for the main tally)
   uint64_t event_tail = 0;   // active-list size below which BGPU_EVENT hands over to the history kernel (0: auto)
@@ -471,11 +471,14 @@ int run_event(bgpu_ctx *c, TransportParams P) {
 // Replicated tallies (transport.cuh, TransportParams::tally_rep): as many copies as fit 64 MB (L2-sized), at most 64;
 // big meshes (8e6 cells) get none -- their deposits are spread over so many addresses that nothing serialises.  The
 // copies are zero between launches (k_fold_tally re-zeroes them).
-// Tally-contention measures (warp-aggregated deposits, replicated tallies) pay where many photons deposit into few
-// cells -- marshak's 25 cells, hot_zone's 5 x 5 hot corner of 40 000 -- and cost where they do not: on the 591 500-cell
-// hohlraum and the 8e6-cell cube the same-cell matching finds nothing to combine (hohlraum streaming cycle +9 %,
-// multi-node share +12 %, big_cube +7 %, hohlraum scattering cycles +2 % without them; profiles/sweep_r01_v15.txt).
-// Unless the host says otherwise (bgpu_set_divergence, bgpu_set_tally_copies) they are on for meshes below 2^17 cells.
+// Tally contention: where many photons deposit into few cells -- marshak's 25 cells, hot_zone's 5 x 5 hot corner of
+// 40 000 -- same-address FP64 reductions serialise in L2, and replicated tallies (up to 64 copies, folded after the
+// launch) are worth 3x.  On the 591 500-cell hohlraum and the 8e6-cell cube they only cost L2 space and a fold: they are
+// on for meshes below 2^17 cells unless the host says otherwise (bgpu_set_tally_copies).  The second measure, combining
+// a warp trip's same-cell deposits by match_any + a shuffle tree (bgpu_set_divergence), is off by default: with the
+// replicated tallies in place its matching costs more than the atomics it saves, on every deck (hot_zone +6...10 %,
+// marshak +7 %, big_cube +7 %, hohlraum streaming cycle +9 %, multi-node share +12 % without it;
+// profiles/sweep_r01_v15.txt).
 bool contended_mesh(const bgpu_ctx *c) { return c->mesh.n_cells < (1u << 17); }
 
 int prepare_tally_copies(bgpu_ctx *c) {
@@ -526,7 +529,7 @@ TransportParams make_params(bgpu_ctx *c, bool writeback_all) {
   // twelve: the short-history multi-node hohlraum (4.8 events per history) runs 3.5 % faster at 4-8, the decks with
   // 30+ events per history want 8-16 (profiles/sweep_r01_v15.txt).  The previous cycle's event count decides.
   if (c->scatter_batch_auto && c->prev_events_per_history > 0.0 && c->prev_events_per_history < 16.0) P.scatter_batch = 6;
-  P.aggregate = c->aggregate >= 0 ? c->aggregate : (contended_mesh(c) ? 1 : 0);
+  P.aggregate = c->aggregate;
   P.writeback_all = writeback_all ? 1 : 0;
   P.stats = c->d_stats;
   P.uniform_groups = (c->uniform_groups && c->closed_form_walk) ? 1 : 0;
@@ -1617,7 +1620,7 @@ int bgpu_set_divergence(bgpu_ctx *c, int scatter_batch, int aggregate_deposits) 
   if (!c) return 1;
   if (scatter_batch > 32) return fail(c, "bgpu_set_divergence: scatter_batch is a lane count (1..32, 0 = keep)");
   if (scatter_batch > 0) { c->scatter_batch = (uint32_t)scatter_batch; c->scatter_batch_auto = false; }
-  if (aggregate_deposits >= 0) c->aggregate = aggregate_deposits ? 1 : 0;  // (< 0 keeps: by mesh size unless set before)
+  if (aggregate_deposits >= 0) c->aggregate = aggregate_deposits ? 1 : 0;
   return 0;
 }
 

@@ -187,8 +187,8 @@ int bgpu_set_launch(bgpu_ctx *ctx, int block_threads, int blocks_per_sm, int chu
  * summation order of the atomic tallies does): scatter_batch = lanes of a warp that must be parked at a scatter before
  * the warp samples them together (1 = sample immediately, 0 = keep the current value; default 12, or 6 when the previous
  * launch's histories averaged fewer than 16 events); aggregate_deposits =
- * 1 combines the same-cell deposits of a warp trip into one pair of atomics, 0 issues them per lane, < 0 keeps the
- * current setting (default: on for meshes below 2^17 cells, where photons crowd into few cells, off above). */
+ * 1 combines the same-cell deposits of a warp trip into one pair of atomics, 0 (default: with replicated tallies in place
+ * the matching costs more than it saves) issues them per lane, < 0 keeps the current setting. */
 int bgpu_set_divergence(bgpu_ctx *ctx, int scatter_batch, int aggregate_deposits);
 /* Replicated tallies of the history kernel (atomic mode): warps deposit into `copies` separate tally arrays that are
  * summed into the tally buffer after the launch, which divides the same-address reduction traffic of hot cells.
