@@ -55,12 +55,24 @@ def make_deck(n_gpus: int, cycles: int, photons_per_gpu: int = PHOTONS_PER_GPU, 
     return d.with_(n_omp_threads=threads, dd_transport_type="REPLICATED")
 
 
-def config_dict(n_gpus: int, photons_per_gpu: int):
+REF_SAMPLE_PHOTONS = 2_000_000  # user photons per cycle of the reference arm's / cpu_baseline's bounded sample
+
+
+def config_dict(n_gpus: int, photons_per_gpu: int, warmup: int, steps: int, ref_photons: int = REF_SAMPLE_PHOTONS):
+    """The same dict in both arms (ours and --impl reference): it names the workload AND says what the CPU arm runs."""
     return {"workload": "3D_hohlraum_single_node (BASELINE configs[2]): 65x65x140 cells, N_GROUPS=30, REPLICATED, "
-                        f"{photons_per_gpu:.0e} user photons per cycle per GPU, dt=0.01, HISTORY algorithm, atomic tallies",
+                        f"{photons_per_gpu:.0e} user photons per cycle per GPU, dt=0.01, HISTORY algorithm, atomic tallies; "
+                        f"a step is one IMC cycle; the deck's 5 cycles are run on at the same dt: cycles 1-{warmup} warm "
+                        f"up, cycles {warmup + 1}-{warmup + steps} are timed (scattering-dominated steady state; cycle 1 "
+                        "is the streaming transient)",
             "photons_per_cycle": photons_per_gpu * n_gpus, "n_cells": 591500, "n_groups": N_GROUPS,
-            "parallelism": f"replicated x{n_gpus} (photons partitioned, one tally all-reduce per cycle)",
-            "l2": "inputs larger than L2 (>= 1 GB of photon state per GPU and cycle; no explicit flush)"}
+            "cycles_timed": [warmup + 1, warmup + steps],
+            "parallelism": f"replicated x{n_gpus} (photons partitioned, one packed tally all-reduce per cycle)",
+            "l2": "inputs larger than L2 (>= 1 GB of photon state per GPU and cycle; no explicit flush)",
+            "cpu_arm_sample_photons_per_cycle": ref_photons,
+            "cpu_arm_note": f"the CPU arms (--impl reference, cpu_baseline) run the same deck and the same cycle window at "
+                            f"{ref_photons} user photons per cycle -- a bounded sample: the full {photons_per_gpu:.0e} "
+                            "would take ~15 s per cycle on 16 cores"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -151,16 +163,21 @@ def run_reference_cpu(cycles: int, photons: int, threads: int, timeout: float = 
             "wall_s": time.time() - t0}
 
 
-def cpu_baseline_block(sample_photons: int, cycles: int = 3):
+def cpu_sample_text(r, photons, warmup, steps, hist, t_tr):
+    return (f"the unmodified reference binary (OpenMP, {r['cores']} threads) on the same deck at {photons} user photons "
+            f"per cycle ({hist // steps} histories per cycle incl. the one-per-cell minimum), cycles 1-{warmup + steps} run, "
+            f"cycles {warmup + 1}-{warmup + steps} quoted: {hist} histories in {t_tr:.2f} s of the reference's own "
+            f"'Transport time' (serial sourcing {sum(r['source_s'][warmup:]):.2f} s extra; whole run {r['wall_s']:.1f} s)")
+
+
+def cpu_baseline_block(sample_photons: int, warmup: int, steps: int):
+    """One protocol for every CPU number of a record: same deck, same cycle window as the timed GPU cycles."""
     threads = host_cores()
-    r = run_reference_cpu(cycles, sample_photons, threads)
-    # cycle 1 is the streaming transient (no scattering yet); quote the later cycles, like the timed GPU cycles
-    hist = sum(r["photons"][1:])
-    secs = sum(r["transport_s"][1:])
+    r = run_reference_cpu(warmup + steps, sample_photons, threads)
+    hist = sum(r["photons"][warmup:])
+    secs = sum(r["transport_s"][warmup:])
     return {"value": hist / secs, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-            "sample": f"same deck with {sample_photons} user photons per cycle, {cycles} cycles, cycles 2-{cycles} quoted "
-                      f"({hist} histories in {secs:.2f} s of the reference's own 'Transport time'; serial sourcing "
-                      f"{sum(r['source_s'][1:]):.2f} s extra; whole run {r['wall_s']:.1f} s)"}
+            "sample": cpu_sample_text(r, sample_photons, warmup, steps, hist, secs)}
 
 
 def reference_arm(args):
@@ -177,11 +194,9 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": hist / t_tr, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tr / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args.gpus, PHOTONS_PER_GPU),
+            "config": config_dict(args.gpus, args.photons, args.warmup, args.steps, sample),
             "cpu_baseline": {"value": hist / t_tr, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                             "sample": f"each step = one cycle of the same deck at {sample} user photons "
-                                       f"(bounded sample of the 1e7-photon workload); transport time as the reference "
-                                       f"reports it"},
+                             "sample": cpu_sample_text(r, sample, args.warmup, args.steps, hist, t_tr)},
             "e2e": {"value": hist / t_all, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -267,6 +282,115 @@ def aos_dropin_block(d, n_groups: int, device: int, repeats: int = 2):
         ctx.close()
 
 
+def parity_check(world: int, rank: int, local: int, dist):
+    """Two cycles of hohlraum_multi (mesh / 5) through exactly the path timed below -- `world` ranks, device mesh,
+    k_mesh_redistribute, the native packed all-reduce, k_mesh_update_temperature -- against the `world`-rank oracle, on
+    every rank: per-photon integers bit for bit, T_e / T_r / tallies 1e-9, conservation 1e-12.  (The oracle is the
+    checker here, outside every timed region; reference src/mesh.h:291-315, src/replicated_driver.h:91-104.)"""
+    import numpy as np
+    import torch
+
+    from branson_b200 import decks, driver, gpu
+    from oracle import port
+    deck = decks.hohlraum_multi(photons=60000, t_stop=0.002, scale=5).with_(dd_transport_type="REPLICATED")
+    tmp = tempfile.mkdtemp(prefix="branson_parity_")
+    d = driver.Driver(deck.write(os.path.join(tmp, f"deck_{rank}.xml")), n_groups=deck.n_groups, rank=rank,
+                      n_ranks=world, device=local, validate=True, mesh_on_device=True)
+    if world > 1:
+        driver.init_nccl(d, dist)
+    view = d.gpu_context()
+    sim = port.OracleSim(deck, n_ranks=world)
+    ok, what, cycles = True, "", 0
+    try:
+        while not sim.finished():
+            cycles += 1
+            sim.cycle(keep_photons=True)
+            rep = d.cycle()
+            post = view.download(gpu.LIST_WORK, counters=True)
+            for k in ("cell", "group", "ctr", "descriptor", "counters"):
+                if not np.array_equal(post[k], sim.get("post/" + k, rank)):
+                    ok, what = False, f"cycle {cycles} rank {rank}: post/{k}"
+            for k in ("abs_E", "track_E", "T_e", "T_r"):
+                want = sim.get(k)
+                if not np.max(np.abs(d.array(k) - want)) <= 1e-9 * np.max(np.abs(want)):
+                    ok, what = False, f"cycle {cycles} rank {rank}: {k}"
+            total = rep["pre_census_E"] + rep["emission_E"] + rep["source_E"]
+            if not abs(rep["rad_conservation"]) <= 1e-12 * total:
+                ok, what = False, f"cycle {cycles} rank {rank}: radiation conservation {rep['rad_conservation']:.3e}"
+            if rep["trans_particles"] != sum(int(sim.get("n_photons", r)[0]) for r in range(world)):
+                ok, what = False, f"cycle {cycles} rank {rank}: global photon count"
+    finally:
+        kind = gpu.comm_info(view._h)["kind"]
+        d.close()
+    if world > 1:
+        flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = bool(flag.item() > 0.5)
+    else:
+        all_ok = ok
+    if not ok:
+        print(f"[bench] PARITY FAILURE: {what}", file=sys.stderr, flush=True)
+    return {"n_ranks": world, "ok": all_ok, "cycles": cycles, "deck": "hohlraum_multi(scale=5), 60000 photons",
+            "against": f"{world}-rank oracle (oracle/imc_oracle.c, pinned to the unmodified reference)",
+            "collective": {gpu.COMM_NONE: "none (1 rank)", gpu.COMM_NCCL: "native ncclAllReduce, one per cycle",
+                           gpu.COMM_LOCAL: "in-process"}[kind],
+            "checked": "per-photon cell/group/rng counter/descriptor/event counters bit-exact on every rank; "
+                       "abs_E, track_E, T_e, T_r 1e-9; radiation conservation 1e-12"}
+
+
+def extra_configs(world: int):
+    from branson_b200 import decks
+    return {
+        # configs[3]: 3D_hohlraum_multi_node.xml forced REPLICATED, 2.5e8 photons over the ranks, dt 0.001, 5 cycles
+        "hohlraum_multi": (decks.hohlraum_multi(photons=250_000_000, t_stop=0.005), 5),
+        # configs[4]: big_cube.xml scaled to 200^3 cells, 1.25e8 photons per GPU (1e9 at 8 GPUs), 5 cycles
+        "big_cube_200": (decks.big_cube(n=200, photons=125_000_000 * world, t_stop=0.005), 5),
+    }
+
+
+def run_extra_config(name, deck, cycles, world, rank, local, dist):
+    """`cycles` cycles of one more BASELINE deck on all ranks: histories of all ranks / the slowest rank's device-timed
+    transport, and / the whole cycle's wall time (barrier to barrier).  The first cycle (streaming transient, first-touch
+    allocations) is reported but not part of the quoted figures."""
+    import torch
+
+    from branson_b200 import driver, gpu
+    tmp = tempfile.mkdtemp(prefix="branson_cfg_")
+    d = driver.Driver(deck.with_(dd_transport_type="REPLICATED").write(os.path.join(tmp, f"{name}_{rank}.xml")),
+                      n_groups=deck.n_groups, rank=rank, n_ranks=world, device=local, mesh_on_device=True)
+    driver.init_nccl(d, dist)
+    rows = []
+    for c in range(cycles):
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[local])
+        t0 = time.perf_counter()
+        r = d.cycle()
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[local])
+        wall = time.perf_counter() - t0
+        g = r["gpu"]
+        v = torch.tensor([g["ms_transport"], wall * 1e3, g["ms_source"], g["ms_census"]], dtype=torch.float64,
+                         device=f"cuda:{local}")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        total = r["pre_census_E"] + r["emission_E"] + r["source_E"]
+        rows.append({"cycle": c + 1, "histories": int(r["trans_particles"]), "ms_transport_max": v[0].item(),
+                     "ms_cycle_wall_max": v[1].item(), "ms_source_max": v[2].item(), "ms_census_max": v[3].item(),
+                     "events_per_history_rank0": g["n_events"] / max(1, g["n_transported"]),
+                     "rad_balance_rel": abs(r["rad_balance_exact"]) / max(1e-300, total)})
+    info = gpu.comm_info(d.gpu_context()._h)
+    d.close()
+    q = rows[1:] if len(rows) > 1 else rows
+    hist = sum(x["histories"] for x in q)
+    return {"deck": name, "n_gpus": world, "photons_per_cycle": deck.photons, "n_groups": deck.n_groups,
+            "n_cells": deck.n_cells, "cycles_quoted": [q[0]["cycle"], q[-1]["cycle"]],
+            "transport_histories_per_s": hist / (sum(x["ms_transport_max"] for x in q) * 1e-3),
+            "whole_cycle_histories_per_s": hist / (sum(x["ms_cycle_wall_max"] for x in q) * 1e-3),
+            "ms_transport_per_cycle": sum(x["ms_transport_max"] for x in q) / len(q),
+            "ms_whole_cycle": sum(x["ms_cycle_wall_max"] for x in q) / len(q),
+            "collectives_per_cycle": info["calls"] / cycles, "max_rad_balance_rel": max(x["rad_balance_rel"] for x in rows),
+            "unit": UNIT, "cycles": rows}
+
+
 def our_arm(args):
     # host physics (calculate_photon_energy / update_temperature) is OpenMP: give each rank its share of the cores
     # (torchrun would otherwise pin every process to OMP_NUM_THREADS=1)
@@ -289,11 +413,17 @@ def our_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
-    comm = None
+    dist = None
     if world > 1:
+        # torch.distributed is launch plumbing here: it carries the NCCL unique id of the drivers' own communicators
+        # (driver.init_nccl) and reduces this script's timing numbers; the cycle's collective is native C++
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        comm = driver.TorchComm(f"cuda:{local}")
+
+    # ---- parity gate of exactly the path that is timed below (N-rank device mesh + native all-reduce) ----
+    parity = None
+    if not args.no_parity_check:
+        parity = parity_check(world, rank, local, dist)
 
     cycles = args.warmup + args.steps
     # one cycle more than is run, so that the state after the last timed cycle still has a time step ahead of it (the
@@ -303,8 +433,9 @@ def our_arm(args):
     xml = deck.write(os.path.join(tmp, f"deck_rank{rank}.xml"))
     on_device = args.mesh == "device"
     d = driver.Driver(xml, n_groups=N_GROUPS, rank=rank, n_ranks=world, device=local,
-                      algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, comm=comm,
-                      mesh_on_device=on_device)
+                      algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, mesh_on_device=on_device)
+    if world > 1:
+        driver.init_nccl(d, dist)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -335,8 +466,9 @@ def our_arm(args):
     if on_device and not args.no_host_mesh_e2e:
         d.close()
         d2 = driver.Driver(xml, n_groups=N_GROUPS, rank=rank, n_ranks=world, device=local,
-                           algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, comm=comm,
-                           mesh_on_device=False)
+                           algorithm=gpu.EVENT if args.algorithm == "event" else gpu.HISTORY, mesh_on_device=False)
+        if world > 1:
+            driver.init_nccl(d2, dist)
         for _ in range(args.warmup):
             d2.cycle()
         sync_all()
@@ -377,7 +509,8 @@ def our_arm(args):
         line = {"metric": METRIC, "value": hist_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config_dict(world, args.photons),
+                "config": config_dict(world, args.photons, args.warmup, args.steps, args.ref_photons),
+                "parity_checked": parity,
                 "e2e": {"value": hist_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * wall_max / args.steps,
                         "path": ("Driver.cycle() with the mesh physics on the device (bgpu_mesh_*): cell state resident "
@@ -427,12 +560,25 @@ def our_arm(args):
                 line["e2e_aos_dropin"] = {"value": None, "unit": UNIT, "path": f"failed: {type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline_block(args.cpu_sample_photons)
+                line["cpu_baseline"] = cpu_baseline_block(args.ref_photons, args.warmup, args.steps)
             except Exception as e:  # the bench line must still be printed
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
     d.close()
+    # BASELINE configs[3] and [4] at their named sizes, N > 1 only: extra keys of the same JSON line
+    extra = None
+    if world > 1 and not args.no_extra_configs:
+        extra = {}
+        for name, (deck_x, cyc_x) in extra_configs(world).items():
+            try:
+                res = run_extra_config(name, deck_x, cyc_x, world, rank, local, dist)
+            except Exception as e:  # the bench line must still be printed
+                res = {"failed": f"{type(e).__name__}: {e}"}
+            extra[name] = res
+    if rank == 0:
+        if extra is not None:
+            line["configs"] = extra
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier(device_ids=[local])
         torch.distributed.destroy_process_group()
@@ -452,9 +598,11 @@ def main():
     ap.add_argument("--mesh", default="device", choices=["device", "host"],
                     help="where calculate_photon_energy / update_temperature run (e2e path)")
     ap.add_argument("--no-host-mesh-e2e", action="store_true", help="skip the second, host-mesh e2e measurement")
-    ap.add_argument("--cpu-sample-photons", type=int, default=1_000_000)
-    ap.add_argument("--ref-photons", type=int, default=400_000,
-                    help="--impl reference: user photons per cycle of the bounded sample")
+    ap.add_argument("--ref-photons", type=int, default=REF_SAMPLE_PHOTONS,
+                    help="user photons per cycle of the CPU arms' bounded sample (--impl reference and cpu_baseline)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the N-rank oracle check before timing")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="N > 1: skip BASELINE configs[3] (hohlraum_multi) and configs[4] (big_cube) after the main run")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

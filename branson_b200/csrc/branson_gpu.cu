@@ -19,6 +19,7 @@
 #include "../../include/branson_gpu.h"
 #include "census.cuh"
 #include "comb.cuh"
+#include "comm_native.cuh"
 #include "common.cuh"
 #include "event.cuh"
 #include "mesh_dev.cuh"
@@ -114,6 +115,13 @@ struct bgpu_ctx {
   double mesh_dt = 0.0;
   uint32_t mesh_step = 0;
   bool mesh_redistributed = false;
+
+  // replicated-mode collectives (comm_native.cuh): the back end this rank's all-reduces go through, the pinned staging
+  // of the rank's scalars and of the tail coming back, a device scratch for host-buffer reductions
+  CommHandle comm;
+  double *h_comm = nullptr;       // pinned: [0, RANK_SCALARS) this rank's row; then the reduced tail + the mesh sums
+  double *d_comm_scratch = nullptr;
+  static constexpr uint64_t COMM_SCRATCH_DOUBLES = 4096;
 
   uint64_t launches = 0;  // kernels launched through this ctx since creation
   bgpu_cycle_stats stats{};
@@ -742,7 +750,7 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
     cudaError_t e__ = (call);                                                                                  \
     if (e__ != cudaSuccess) {                                                                                  \
       fail(nullptr, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, #call);           \
-      delete c;                                                                                                \
+      bgpu_destroy(c); /* frees whatever has been created so far (every member is null-checked) */            \
       return 1;                                                                                                \
     }                                                                                                          \
   } while (0)
@@ -789,7 +797,7 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   if (!cap) cap = (uint64_t)(1.25 * (double)d->n_user_photons / (double)c->n_ranks) + 1024;
   if (ensure_work(c, cap, 0)) {
     g_create_error = c->err;
-    delete c;
+    bgpu_destroy(c);
     return 1;
   }
 #undef CUC
@@ -817,6 +825,9 @@ void bgpu_destroy(bgpu_ctx *c) {
                   c->d_region_of_cell, c->d_mesh, c->d_tile_sums, c->d_mesh_sums};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  c->comm.reset();
+  if (c->h_comm) cudaFreeHost(c->h_comm);
+  if (c->d_comm_scratch) cudaFree(c->d_comm_scratch);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -1008,13 +1019,7 @@ MeshPhysParams mesh_params(bgpu_ctx *c) {
   return P;
 }
 
-int mesh_fetch_sums(bgpu_ctx *c, uint32_t q_mask, bgpu_mesh_sums *out) {
-  ++c->launches;
-  k_mesh_final_sums<<<1, 32, 0, c->stream>>>(c->d_tile_sums, c->mesh_tiles, q_mask, c->d_mesh_sums);
-  CU(c, cudaGetLastError());
-  double h[MS_N];
-  CU(c, cudaMemcpyAsync(h, c->d_mesh_sums, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+void unpack_sums(const double *h, uint32_t q_mask, bgpu_mesh_sums *out) {
   if (q_mask & (1u << MS_PRE_MAT)) out->pre_mat_E = h[MS_PRE_MAT];
   if (q_mask & (1u << MS_EMISSION)) out->emission_E = h[MS_EMISSION];
   if (q_mask & (1u << MS_CENSUS)) out->census_E = h[MS_CENSUS];
@@ -1022,6 +1027,22 @@ int mesh_fetch_sums(bgpu_ctx *c, uint32_t q_mask, bgpu_mesh_sums *out) {
   if (q_mask & (1u << MS_TOTAL)) out->total_photon_E = h[MS_TOTAL];
   if (q_mask & (1u << MS_ABS)) out->absorbed_E = h[MS_ABS];
   if (q_mask & (1u << MS_POST_MAT)) out->post_mat_E = h[MS_POST_MAT];
+}
+
+// the tile sums -> d_mesh_sums[block][q] for `n_blocks` rank blocks (no host synchronisation)
+int mesh_final_sums_async(bgpu_ctx *c, uint32_t q_mask, uint32_t n_blocks) {
+  ++c->launches;
+  k_mesh_final_sums<<<n_blocks, 32, 0, c->stream>>>(c->d_tile_sums, c->mesh_tiles, q_mask, c->d_mesh_sums);
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
+int mesh_fetch_sums(bgpu_ctx *c, uint32_t q_mask, bgpu_mesh_sums *out, uint32_t n_blocks = 1) {
+  if (mesh_final_sums_async(c, q_mask, n_blocks)) return 1;
+  std::vector<double> h((size_t)MS_N * n_blocks);
+  CU(c, cudaMemcpyAsync(h.data(), c->d_mesh_sums, 8 * h.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t b = 0; b < n_blocks; ++b) unpack_sums(h.data() + (size_t)MS_N * b, q_mask, out + b);
   return 0;
 }
 }  // namespace
@@ -1040,8 +1061,9 @@ int bgpu_mesh_init(bgpu_ctx *c, uint32_t n_regions, const bgpu_region *regions, 
     c->mesh_tiles = (uint32_t)((nc + MESH_TILE - 1) / MESH_TILE);
     CU(c, cudaMalloc((void **)&c->d_region_of_cell, 4 * nc));
     CU(c, cudaMalloc((void **)&c->d_mesh, 8 * nc * MA_N));
-    CU(c, cudaMalloc((void **)&c->d_tile_sums, 8ull * MS_N * c->mesh_tiles));
-    CU(c, cudaMalloc((void **)&c->d_mesh_sums, 8 * MS_N));
+    // (one block of sums per rank: k_mesh_redistribute forms every rank's totals, mesh_dev.cuh)
+    CU(c, cudaMalloc((void **)&c->d_tile_sums, 8ull * MS_N * c->mesh_tiles * c->n_ranks));
+    CU(c, cudaMalloc((void **)&c->d_mesh_sums, 8ull * MS_N * c->n_ranks));
   }
   if (c->d_regions) CU(c, cudaFree(c->d_regions));
   CU(c, cudaMalloc((void **)&c->d_regions, sizeof(RegionDev) * n_regions));
@@ -1088,10 +1110,56 @@ int bgpu_mesh_redistribute(bgpu_ctx *c, double global_source_E, bgpu_mesh_sums *
   MeshPhysParams P = mesh_params(c);
   P.global_source_E = global_source_E;
   ++c->launches;
-  k_mesh_redistribute<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(P);
+  k_mesh_redistribute<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(P, nullptr);
   CU(c, cudaGetLastError());
   c->mesh_redistributed = true;
-  return mesh_fetch_sums(c, (1u << MS_EMISSION) | (1u << MS_CENSUS) | (1u << MS_SOURCE) | (1u << MS_TOTAL), sums);
+  // (this rank's block of the per-rank sums)
+  std::vector<bgpu_mesh_sums> all((size_t)c->n_ranks);
+  const uint32_t mask = (1u << MS_EMISSION) | (1u << MS_CENSUS) | (1u << MS_SOURCE) | (1u << MS_TOTAL);
+  if (mesh_fetch_sums(c, mask, all.data(), (uint32_t)c->n_ranks)) return 1;
+  const bgpu_mesh_sums &mine = all[(size_t)c->rank];
+  sums->emission_E = mine.emission_E;
+  sums->census_E = mine.census_E;
+  sums->source_E = mine.source_E;
+  sums->total_photon_E = mine.total_photon_E;
+  return 0;
+}
+
+// calculate_photon_energy for a replicated run without its collectives (see k_mesh_redistribute): one launch chain, one
+// host synchronisation; rank_sums[r] = rank r's totals after the redistribution (pre_mat_E is the same for all)
+int bgpu_mesh_calculate_photon_energy_replicated(bgpu_ctx *c, double dt, uint32_t step, bgpu_mesh_sums *rank_sums) {
+  if (!c || !rank_sums) return fail(c, "bgpu_mesh_calculate_photon_energy_replicated: null argument");
+  if (!c->mesh_ready) return fail(c, "bgpu_mesh_calculate_photon_energy_replicated: call bgpu_mesh_init first");
+  if (c->n_ranks == 1) return bgpu_mesh_calculate_photon_energy(c, dt, step, rank_sums);
+  CU(c, cudaSetDevice(c->device));
+  c->mesh_dt = dt;
+  c->mesh_step = step;
+  const MeshPhysParams P = mesh_params(c);
+  ++c->launches;
+  k_mesh_energy<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(P);
+  const uint32_t m_energy = (1u << MS_PRE_MAT) | (1u << MS_EMISSION) | (1u << MS_CENSUS) | (1u << MS_SOURCE) |
+                            (1u << MS_TOTAL);
+  if (mesh_final_sums_async(c, m_energy, 1)) return 1;
+  double pre_mat = 0.0;
+  CU(c, cudaMemcpyAsync(&pre_mat, c->d_mesh_sums + MS_PRE_MAT, 8, cudaMemcpyDeviceToHost, c->stream));
+  ++c->launches;
+  k_mesh_redistribute<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(P, c->d_mesh_sums);
+  // every group gets the cell's gray opacity (Cell::set_op_a / set_op_s, src/cell.h:260-275)
+  ++c->launches;
+  k_expand_groups<<<grid_for((uint64_t)c->mesh.n_cells * c->mesh.G, 256), 256, 0, c->stream>>>(
+      c->mesh.n_cells, c->mesh.G, P.op_a, P.op_s, c->d_opa, c->d_ops);
+  ++c->launches;
+  k_fill_cellrec<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>(c->mesh.n_cells, c->mesh.G, c->d_f, c->d_opa,
+                                                                        c->d_ops, c->d_cellrec);
+  CU(c, cudaGetLastError());
+  c->have_cell_data = true;
+  c->uniform_groups = true;
+  c->mesh_redistributed = true;
+  for (int r = 0; r < c->n_ranks; ++r) rank_sums[r] = bgpu_mesh_sums{};
+  const uint32_t m_red = (1u << MS_EMISSION) | (1u << MS_CENSUS) | (1u << MS_SOURCE) | (1u << MS_TOTAL);
+  if (mesh_fetch_sums(c, m_red, rank_sums, (uint32_t)c->n_ranks)) return 1;  // (synchronises: pre_mat has arrived)
+  for (int r = 0; r < c->n_ranks; ++r) rank_sums[r].pre_mat_E = pre_mat;
+  return 0;
 }
 
 int bgpu_mesh_source(bgpu_ctx *c, uint32_t cycle, double total_E, uint64_t *n_new_out, uint64_t *n_total_out) {
@@ -1189,22 +1257,208 @@ int bgpu_get_tallies(bgpu_ctx *c, double *abs_E, double *track_E, bgpu_cycle_sta
   return 0;
 }
 
+}  // extern "C"
+namespace {
+// the tally buffer with room for `extra` doubles behind the 2 * n_cells tallies (contents kept)
+int ensure_tally_extra(bgpu_ctx *c, uint64_t extra) {
+  const uint64_t nc = c->mesh.n_cells;
+  if (extra <= c->tally_extra) return 0;
+  double *p = nullptr;
+  CU(c, cudaMalloc((void **)&p, 8 * (2 * nc + extra)));
+  CU(c, cudaMemcpyAsync(p, c->d_tally, 8 * (2 * nc + c->tally_extra), cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaMemsetAsync(p + 2 * nc + c->tally_extra, 0, 8 * (extra - c->tally_extra), c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaFree(c->d_tally));
+  c->d_tally = p;
+  c->tally_extra = extra;
+  return 0;
+}
+
+int ensure_comm_buffers(bgpu_ctx *c) {
+  const uint64_t tail = (uint64_t)c->n_ranks * BGPU_RANK_SCALARS;
+  if (ensure_tally_extra(c, tail)) return 1;
+  if (!c->h_comm) CU(c, cudaHostAlloc((void **)&c->h_comm, 8 * (BGPU_RANK_SCALARS + tail + MS_N + 64), cudaHostAllocDefault));
+  if (!c->d_comm_scratch) CU(c, cudaMalloc((void **)&c->d_comm_scratch, 8 * bgpu_ctx::COMM_SCRATCH_DOUBLES));
+  return 0;
+}
+
+// in-place reduction of n device doubles over the ranks of this ctx's communicator, ordered on the ctx stream
+int comm_allreduce_device(bgpu_ctx *c, double *ptr, uint64_t n, int op /* ncclRedOp_t value: 0 sum, 2 max, 3 min */) {
+  if (c->n_ranks == 1) return 0;
+  if (c->comm.kind == COMM_NCCL) {
+    NcclApi &api = NcclApi::get();
+    const ncclResult_t r = api.AllReduce(ptr, ptr, n, ncclDouble, (ncclRedOp_t)op, c->comm.nccl, c->stream);
+    if (r != ncclSuccess) return fail(c, "ncclAllReduce: %s", api.GetErrorString(r));
+  } else if (c->comm.kind == COMM_LOCAL) {
+    const char *e = local_allreduce(*c->comm.local, c->rank, ptr, n, op, c->stream);
+    if (e) return fail(c, "in-process all-reduce: %s", e);
+  } else {
+    return fail(c, "rank %d of %d has no communicator (bgpu_comm_init_rank / bgpu_comm_init_local)", c->rank, c->n_ranks);
+  }
+  c->comm.bytes += 8 * n;
+  ++c->comm.calls;
+  return 0;
+}
+
+// The cycle's one collective, enqueued on the ctx stream without a host synchronisation: this rank's row of the tail is
+// filled from `rank_scalars`, the others are zeroed, and {tallies, tail} are summed in place over the ranks.
+int reduce_tallies_async(bgpu_ctx *c, const double *rank_scalars) {
+  if (ensure_comm_buffers(c)) return 1;
+  const uint64_t nc = c->mesh.n_cells, tail = (uint64_t)c->n_ranks * BGPU_RANK_SCALARS;
+  double *d_tail = c->d_tally + 2 * nc;
+  for (int i = 0; i < BGPU_RANK_SCALARS; ++i) c->h_comm[i] = rank_scalars ? rank_scalars[i] : 0.0;
+  CU(c, cudaMemsetAsync(d_tail, 0, 8 * tail, c->stream));
+  CU(c, cudaMemcpyAsync(d_tail + (uint64_t)c->rank * BGPU_RANK_SCALARS, c->h_comm, 8 * BGPU_RANK_SCALARS,
+                        cudaMemcpyHostToDevice, c->stream));
+  return comm_allreduce_device(c, c->d_tally, 2 * nc + tail, 0);
+}
+}  // namespace
+extern "C" {
+
 int bgpu_tally_buffer(bgpu_ctx *c, uint64_t extra, void **device_ptr, uint64_t *n_doubles) {
   if (!c || !device_ptr || !n_doubles) return fail(c, "bgpu_tally_buffer: null argument");
   CU(c, cudaSetDevice(c->device));
-  const uint64_t nc = c->mesh.n_cells;
-  if (extra > c->tally_extra) {
-    double *p = nullptr;
-    CU(c, cudaMalloc((void **)&p, 8 * (2 * nc + extra)));
-    CU(c, cudaMemcpyAsync(p, c->d_tally, 8 * (2 * nc + c->tally_extra), cudaMemcpyDeviceToDevice, c->stream));
-    CU(c, cudaMemsetAsync(p + 2 * nc + c->tally_extra, 0, 8 * (extra - c->tally_extra), c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    CU(c, cudaFree(c->d_tally));
-    c->d_tally = p;
-    c->tally_extra = extra;
-  }
+  if (ensure_tally_extra(c, extra)) return 1;
   *device_ptr = c->d_tally;
-  *n_doubles = 2 * nc + extra;
+  *n_doubles = 2 * (uint64_t)c->mesh.n_cells + extra;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// replicated-mode collectives (comm_native.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+int bgpu_comm_unique_id(char id[BGPU_COMM_ID_BYTES]) {
+  static_assert(BGPU_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "unique id size");
+  if (!id) return fail(nullptr, "bgpu_comm_unique_id: null argument");
+  NcclApi &api = NcclApi::get();
+  if (!api.ok()) return fail(nullptr, "bgpu_comm_unique_id: %s", api.error.c_str());
+  ncclUniqueId u;
+  const ncclResult_t r = api.GetUniqueId(&u);
+  if (r != ncclSuccess) return fail(nullptr, "ncclGetUniqueId: %s", api.GetErrorString(r));
+  memcpy(id, u.internal, BGPU_COMM_ID_BYTES);
+  return 0;
+}
+
+int bgpu_comm_init_rank(bgpu_ctx *c, const char id[BGPU_COMM_ID_BYTES]) {
+  if (!c || !id) return fail(c, "bgpu_comm_init_rank: null argument");
+  if (c->n_ranks == 1) return 0;
+  NcclApi &api = NcclApi::get();
+  if (!api.ok()) return fail(c, "bgpu_comm_init_rank: %s", api.error.c_str());
+  CU(c, cudaSetDevice(c->device));
+  c->comm.reset();
+  ncclUniqueId u;
+  memcpy(u.internal, id, BGPU_COMM_ID_BYTES);
+  const ncclResult_t r = api.CommInitRank(&c->comm.nccl, c->n_ranks, u, c->rank);
+  if (r != ncclSuccess) return fail(c, "ncclCommInitRank(rank %d of %d): %s", c->rank, c->n_ranks, api.GetErrorString(r));
+  c->comm.kind = COMM_NCCL;
+  return ensure_comm_buffers(c);
+}
+
+int bgpu_comm_init_local(bgpu_ctx **ctxs, int n) {
+  if (!ctxs || n < 1) return fail(nullptr, "bgpu_comm_init_local: null argument");
+  bool same_device = true, distinct = true;
+  for (int r = 0; r < n; ++r) {
+    if (!ctxs[r]) return fail(nullptr, "bgpu_comm_init_local: null ctx");
+    if (ctxs[r]->rank != r || ctxs[r]->n_ranks != n)
+      return fail(ctxs[r], "bgpu_comm_init_local: ctxs[%d] was created as rank %d of %d", r, ctxs[r]->rank, ctxs[r]->n_ranks);
+    same_device = same_device && ctxs[r]->device == ctxs[0]->device;
+    for (int q = 0; q < r; ++q) distinct = distinct && ctxs[q]->device != ctxs[r]->device;
+  }
+  if (n == 1) return 0;
+  for (int r = 0; r < n; ++r) ctxs[r]->comm.reset();
+  if (distinct) {
+    // one GPU per rank: NCCL over NVLink (one process, one host thread per rank)
+    NcclApi &api = NcclApi::get();
+    if (!api.ok()) return fail(ctxs[0], "bgpu_comm_init_local: %s", api.error.c_str());
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int r = 0; r < n; ++r) devs[r] = ctxs[r]->device;
+    const ncclResult_t e = api.CommInitAll(comms.data(), n, devs.data());
+    if (e != ncclSuccess) return fail(ctxs[0], "ncclCommInitAll: %s", api.GetErrorString(e));
+    for (int r = 0; r < n; ++r) {
+      ctxs[r]->comm.nccl = comms[r];
+      ctxs[r]->comm.kind = COMM_NCCL;
+    }
+  } else if (same_device) {
+    if (n > LOCAL_MAX_RANKS) return fail(ctxs[0], "bgpu_comm_init_local: at most %d ranks on one device", LOCAL_MAX_RANKS);
+    auto g = std::make_shared<LocalGroup>();
+    g->n_ranks = n;
+    g->device = ctxs[0]->device;
+    CU(ctxs[0], cudaSetDevice(g->device));
+    for (int r = 0; r < n; ++r) CU(ctxs[0], cudaEventCreateWithFlags(&g->ev_ready[r], cudaEventDisableTiming));
+    CU(ctxs[0], cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
+    for (int r = 0; r < n; ++r) {
+      ctxs[r]->comm.local = g;
+      ctxs[r]->comm.kind = COMM_LOCAL;
+    }
+  } else {
+    return fail(ctxs[0], "bgpu_comm_init_local: ranks must sit on distinct devices (NCCL) or all on one (in-process sum)");
+  }
+  for (int r = 0; r < n; ++r) {
+    CU(ctxs[r], cudaSetDevice(ctxs[r]->device));
+    if (ensure_comm_buffers(ctxs[r])) return 1;
+  }
+  return 0;
+}
+
+int bgpu_comm_info(const bgpu_ctx *c, int *kind, uint64_t *calls, uint64_t *bytes) {
+  if (!c) return 1;
+  if (kind) *kind = c->comm.kind;
+  if (calls) *calls = c->comm.calls;
+  if (bytes) *bytes = c->comm.bytes;
+  return 0;
+}
+
+int bgpu_comm_allreduce_host(bgpu_ctx *c, double *buf, uint64_t n, int op) {
+  if (!c || (!buf && n)) return fail(c, "bgpu_comm_allreduce_host: null argument");
+  if (op != BGPU_OP_SUM && op != BGPU_OP_MAX && op != BGPU_OP_MIN) return fail(c, "bgpu_comm_allreduce_host: unknown op %d", op);
+  if (c->n_ranks == 1 || n == 0) return 0;
+  CU(c, cudaSetDevice(c->device));
+  if (ensure_comm_buffers(c)) return 1;
+  const int nccl_op = op == BGPU_OP_SUM ? 0 : (op == BGPU_OP_MAX ? 2 : 3);
+  for (uint64_t off = 0; off < n; off += bgpu_ctx::COMM_SCRATCH_DOUBLES) {
+    const uint64_t m = std::min<uint64_t>(bgpu_ctx::COMM_SCRATCH_DOUBLES, n - off);
+    CU(c, cudaMemcpyAsync(c->d_comm_scratch, buf + off, 8 * m, cudaMemcpyHostToDevice, c->stream));
+    if (comm_allreduce_device(c, c->d_comm_scratch, m, nccl_op)) return 1;
+    CU(c, cudaMemcpyAsync(buf + off, c->d_comm_scratch, 8 * m, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int bgpu_comm_allreduce_tallies(bgpu_ctx *c, const double *rank_scalars, double *all_scalars) {
+  if (!c) return fail(c, "bgpu_comm_allreduce_tallies: null ctx");
+  CU(c, cudaSetDevice(c->device));
+  if (reduce_tallies_async(c, rank_scalars)) return 1;
+  const uint64_t tail = (uint64_t)c->n_ranks * BGPU_RANK_SCALARS;
+  double *h_tail = c->h_comm + BGPU_RANK_SCALARS;
+  CU(c, cudaMemcpyAsync(h_tail, c->d_tally + 2ull * c->mesh.n_cells, 8 * tail, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (all_scalars) memcpy(all_scalars, h_tail, 8 * tail);
+  return 0;
+}
+
+int bgpu_mesh_finish_cycle(bgpu_ctx *c, const double *rank_scalars, double *all_scalars, bgpu_mesh_sums *sums) {
+  if (!c || !sums) return fail(c, "bgpu_mesh_finish_cycle: null argument");
+  if (!c->mesh_ready) return fail(c, "bgpu_mesh_finish_cycle: call bgpu_mesh_init first");
+  CU(c, cudaSetDevice(c->device));
+  // tallies + tail summed over the ranks; src/replicated_driver.h:91-94 and the reductions of src/imc_state.h:207-252
+  if (reduce_tallies_async(c, rank_scalars)) return 1;
+  // mesh.update_temperature (src/replicated_driver.h:96) consumes the reduced tallies in place, stream-ordered
+  const MeshPhysParams P = mesh_params(c);
+  ++c->launches;
+  k_mesh_update_temperature<<<c->mesh_tiles, MESH_TILE_THREADS, 0, c->stream>>>(
+      P, c->mesh_redistributed ? P.E_emission_global : P.E_emission);
+  CU(c, cudaGetLastError());
+  const uint32_t mask = (1u << MS_ABS) | (1u << MS_POST_MAT);
+  if (mesh_final_sums_async(c, mask, 1)) return 1;
+  const uint64_t tail = (uint64_t)c->n_ranks * BGPU_RANK_SCALARS;
+  double *h_tail = c->h_comm + BGPU_RANK_SCALARS, *h_sums = h_tail + tail;
+  CU(c, cudaMemcpyAsync(h_tail, c->d_tally + 2ull * c->mesh.n_cells, 8 * tail, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h_sums, c->d_mesh_sums, 8 * MS_N, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));  // the cycle's one host synchronisation after transport
+  if (all_scalars) memcpy(all_scalars, h_tail, 8 * tail);
+  unpack_sums(h_sums, mask, sums);
   return 0;
 }
 
@@ -1251,7 +1505,7 @@ int aos_copiers() {
   return std::min(AOS_MAX_COPIERS, std::max(1, n));
 }
 
-int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
+int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n, uint64_t *bad_out) {
   if (!c->s_in) {
     CU(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -1278,22 +1532,28 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     const uint64_t first = (uint64_t)j * chunks_per_slice;
     return std::min<uint64_t>(chunks_per_slice, n_chunks - first);
   };
+  // every event of the call lives in one holder, destroyed on every return path
+  struct EventBag {
+    std::vector<cudaEvent_t> all;
+    cudaError_t make(cudaEvent_t &e) {
+      const cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (r == cudaSuccess) all.push_back(e);
+      return r;
+    }
+    ~EventBag() {
+      for (cudaEvent_t e : all) cudaEventDestroy(e);
+    }
+  } bag;
   std::vector<cudaEvent_t> ev_in(n_slices), ev_done(n_slices);
   std::vector<cudaEvent_t> ev_slot((size_t)2 * AOS_COPIERS * AOS_SLOTS);
-  for (auto &e : ev_in) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto &e : ev_done) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto &e : ev_slot) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : ev_in) CU(c, bag.make(e));
+  for (auto &e : ev_done) CU(c, bag.make(e));
+  for (auto &e : ev_slot) CU(c, bag.make(e));
   cudaEvent_t ev_ready;
-  CU(c, cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
-  auto destroy_events = [&]() {
-    cudaEventDestroy(ev_ready);
-    for (auto &e : ev_in) cudaEventDestroy(e);
-    for (auto &e : ev_done) cudaEventDestroy(e);
-    for (auto &e : ev_slot) cudaEventDestroy(e);
-  };
+  CU(c, bag.make(ev_ready));
   uint8_t *d_aos = (uint8_t *)c->scr_aos.p;
   TransportParams P0 = make_params(c, true);
-  if (prepare_tally_copies(c)) { destroy_events(); return 1; }
+  if (prepare_tally_copies(c)) return 1;
   if (c->tally_copies_live > 1) {
     P0.tally_rep = (double2 *)c->scr_tally_rep.p;
     P0.tally_copies = c->tally_copies_live;
@@ -1303,6 +1563,7 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
   for (auto &u : uploaded) u.store(0, std::memory_order_relaxed);
   std::atomic<uint32_t> issued{0};  // slices whose kernels (and ev_done) have been enqueued
   std::atomic<int> abort_flag{0};
+  std::atomic<uint64_t> bad_rng{0};  // photons whose RNG seed / key-high words differ from the ctx's
   std::atomic<int> worker_err{(int)cudaSuccess};
   auto fail_worker = [&](cudaError_t e) {
     int expect = (int)cudaSuccess;
@@ -1330,6 +1591,20 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
       uint64_t off, cnt;
       chunk_range(i, off, cnt);
       memcpy(buf[k], photons + 120 * off, 120 * cnt);
+      {
+        // The RNG words the device does not carry (counter high word = seed << 32, key high word = 0; src/RNG.h:318-330)
+        // are checked HERE, on the staged copy, before the chunk can reach the device: a slice holding a photon of
+        // another seed is never transported, so it is never written back over the caller's vector (slices in front
+        // of it, whose photons were valid, may already be final when the call fails).
+        const uint64_t *w = (const uint64_t *)buf[k];
+        uint64_t bad = 0;
+        for (uint64_t q = 0; q < cnt; ++q) bad += (w[15 * q + 12] != c->ctr_hi) | (w[15 * q + 14] != 0ull);
+        if (bad) {
+          bad_rng.fetch_add(bad, std::memory_order_relaxed);
+          abort_flag.store(1, std::memory_order_release);
+          return;
+        }
+      }
       e = cudaMemcpyAsync(d_aos + 120 * off, buf[k], 120 * cnt, cudaMemcpyHostToDevice, c->s_in);
       if (e == cudaSuccess) e = cudaEventRecord(ev, c->s_in);
       used[k] = true;
@@ -1343,7 +1618,7 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
     uint8_t *buf[AOS_SLOTS];
     for (int k = 0; k < AOS_SLOTS; ++k)
       buf[k] = (uint8_t *)c->h_stage + slot_bytes * (size_t)((AOS_COPIERS + t) * AOS_SLOTS + k);
-    uint64_t pend_off[AOS_SLOTS], pend_cnt[AOS_SLOTS];
+    uint64_t pend_off[AOS_SLOTS] = {}, pend_cnt[AOS_SLOTS] = {};
     bool pending[AOS_SLOTS] = {};
     auto drain = [&](int k) {
       if (!pending[k] || e != cudaSuccess) return;
@@ -1355,10 +1630,12 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
       const uint64_t i = next_down.fetch_add(1, std::memory_order_relaxed);
       if (i >= n_chunks) break;
       const uint32_t j = (uint32_t)(i / chunks_per_slice);
+      bool stop = false;
       while (issued.load(std::memory_order_acquire) <= j) {
-        if (abort_flag.load(std::memory_order_acquire)) return;
+        if (abort_flag.load(std::memory_order_acquire)) { stop = true; break; }
         std::this_thread::yield();
       }
+      if (stop) break;  // (the copies already in flight are still drained into the caller's vector below)
       const int k = turn % AOS_SLOTS;
       drain(k);
       if (e != cudaSuccess) break;
@@ -1445,7 +1722,12 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n) {
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_in);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_out);
-  destroy_events();
+  *bad_out = bad_rng.load();
+  if (*bad_out) {  // reported by the caller; the streams are drained first
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->s_k2);
+    return 0;
+  }
   if (e != cudaSuccess) return fail(c, "bgpu_transport_photons_aos: %s", cudaGetErrorString(e));
   if (worker_err.load() != (int)cudaSuccess)
     return fail(c, "bgpu_transport_photons_aos (copy thread): %s", cudaGetErrorString((cudaError_t)worker_err.load()));
@@ -1469,13 +1751,11 @@ int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cel
   c->n_new = n;
   const bool pipelined = algorithm == BGPU_HISTORY && tally_mode == BGPU_TALLY_ATOMIC && n >= (1ull << 21);
   if (n && pipelined) {
-    if (transport_aos_pipelined(c, (uint8_t *)photons, n)) return 1;
-    unsigned long long bad = 0;
-    CU(c, cudaMemcpyAsync(&bad, c->d_stats + ST_BAD_RNG, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    uint64_t bad = 0;
+    if (transport_aos_pipelined(c, (uint8_t *)photons, n, &bad)) return 1;
     if (bad)
-      return fail(c, "bgpu_transport_photons_aos: %llu photons carry an RNG seed/spawn word different from the ctx seed",
-                  bad);
+      return fail(c, "bgpu_transport_photons_aos: %llu photons carry an RNG seed/spawn word different from the ctx seed "
+                     "(their slices were not transported)", (unsigned long long)bad);
   } else if (n) {
     CU(c, cudaMemcpyAsync(c->scr_aos.p, photons, 120 * n, cudaMemcpyHostToDevice, c->stream));
     ++c->launches;
@@ -1494,7 +1774,19 @@ int bgpu_transport_photons_aos(bgpu_ctx *c, void *photons, uint64_t n, void *cel
     CU(c, cudaMemcpyAsync(photons, c->scr_aos.p, 120 * n, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(c, cudaMemcpyAsync(cell_tallies, c->d_tally, 16 * nc, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long st[ST_COUNT] = {};
+  CU(c, cudaMemcpyAsync(st, c->d_stats, 8 * ST_COUNT, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  // this call's statistics (no post-processing here: census / exit sums are the caller's, src/replicated_transport.h)
+  c->stats = bgpu_cycle_stats{};
+  c->stats.n_new = c->stats.n_transported = n;
+  c->stats.n_events = st[ST_EVENTS];
+  c->stats.n_scatters = st[ST_SCATTERS];
+  c->stats.n_crossings = st[ST_CROSSINGS];
+  c->stats.n_reflections = st[ST_REFLECTIONS];
+  c->stats.n_deposits = st[ST_DEPOSITS];
+  c->stats.n_group_lookups = st[ST_LOOKUPS];
+  c->stats.n_launches = c->launches;
   return 0;
 }
 

@@ -2,8 +2,8 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
-#define BHOST_COMM_DEFINED
 #include "comm.h"
 #include "../../../include/branson_host.h"
 #include "gpu_setup.h"
@@ -76,6 +76,36 @@ bhost_driver *bhost_create(const char *xml_path, int rank, int n_ranks, const bh
 }
 
 void bhost_destroy(bhost_driver *d) { delete d; }
+
+int bhost_comm_unique_id(char id[BGPU_COMM_ID_BYTES]) { return bgpu_comm_unique_id(id); }
+
+int bhost_comm_init_rank(bhost_driver *d, const char id[BGPU_COMM_ID_BYTES]) {
+  if (!d || !d->gpu) return 1;
+  if (bgpu_comm_init_rank(d->gpu->get_ctx(), id)) {
+    d->err = bgpu_last_error(d->gpu->get_ctx());
+    return 1;
+  }
+  d->comm->attach_native(d->gpu->get_ctx());
+  return 0;
+}
+
+int bhost_comm_init_local(bhost_driver **drivers, int n) {
+  if (!drivers || n < 1) return 1;
+  std::vector<bgpu_ctx *> ctxs((size_t)n);
+  for (int r = 0; r < n; ++r) {
+    if (!drivers[r] || !drivers[r]->gpu) return 1;
+    ctxs[(size_t)r] = drivers[r]->gpu->get_ctx();
+  }
+  if (bgpu_comm_init_local(ctxs.data(), n)) {
+    for (int r = 0; r < n; ++r) {
+      const char *e = bgpu_last_error(ctxs[(size_t)r]);
+      drivers[r]->err = (e && *e) ? e : bgpu_last_error(nullptr);
+    }
+    return 1;
+  }
+  for (int r = 0; r < n; ++r) drivers[r]->comm->attach_native(ctxs[(size_t)r]);
+  return 0;
+}
 const char *bhost_last_error(const bhost_driver *d) { return d ? d->err.c_str() : "null driver"; }
 int bhost_finished(const bhost_driver *d) { return d && d->state->finished() ? 1 : 0; }
 
@@ -145,7 +175,8 @@ int bhost_get_array(const bhost_driver *d, const char *name, const double **data
     } catch (const std::exception &) {
       return 1;
     }
-  } else if (k == "T_e") v = &m.get_T_e();
+  } else try {
+    if (k == "T_e") v = &m.get_T_e();
   else if (k == "T_r") v = &m.get_T_r();
   else if (k == "T_s") v = &m.get_T_s();
   else if (k == "f") v = &m.get_f();
@@ -159,6 +190,9 @@ int bhost_get_array(const bhost_driver *d, const char *name, const double **data
   else if (k == "z_faces") v = &m.get_z_faces();
   else if (k == "abs_E" && d->driver) v = &d->driver->get_last_abs_E();
   else if (k == "track_E" && d->driver) v = &d->driver->get_last_track_E();
+  } catch (const std::exception &) {
+    return 1;
+  }
   if (!v) return 1;
   *data = v->data();
   *n = v->size();

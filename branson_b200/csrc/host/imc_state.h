@@ -63,14 +63,24 @@ public:
     comm.min(&tmin, 1);
     uint64_t u[2] = {trans_particles, census_size};
     comm.sum(u, 2);
+    set_global_sums(d, u[0], u[1], tmax, tmin);
+    finish_conservation(print);
+  }
+
+  // The same report from values that are already global: the device-mesh driver receives every rank's scalars with the
+  // cycle's one all-reduce and forms these sums itself, in rank order (csrc/comm_native.cuh).
+  // d = {absorbed, emission, source, pre_census, pre_mat, post_census, post_mat, exit}
+  void set_global_sums(const double d[8], uint64_t trans, uint64_t census, double tmax, double tmin) {
     g_absorbed_E = d[0]; g_emission_E = d[1]; g_source_E = d[2]; g_pre_census_E = d[3];
     g_pre_mat_E = d[4]; g_post_census_E = d[5]; g_post_mat_E = d[6]; g_exit_E = d[7];
-    g_trans_particles = u[0];
-    g_census_size = u[1];
-    rad_conservation = (g_absorbed_E + g_post_census_E + g_exit_E) - (g_pre_census_E + g_emission_E + g_source_E);
-    mat_conservation = g_post_mat_E - (g_pre_mat_E + g_absorbed_E - g_emission_E);
+    g_trans_particles = trans;
+    g_census_size = census;
     max_transport_time = tmax;
     min_transport_time = tmin;
+  }
+  void finish_conservation(bool print) {
+    rad_conservation = (g_absorbed_E + g_post_census_E + g_exit_E) - (g_pre_census_E + g_emission_E + g_source_E);
+    mat_conservation = g_post_mat_E - (g_pre_mat_E + g_absorbed_E - g_emission_E);
     total_trans_particles += g_trans_particles;
     if (rank == 0) {
       if (print) {
@@ -86,8 +96,9 @@ public:
         cout << "Material conservation: " << mat_conservation << endl;
         cout << "Transport time max/min: " << max_transport_time << "/" << min_transport_time << endl;
       }
-      total_transport_time += max_transport_time;
     }
+    // (every rank keeps the run's transport time; the reference accumulates it on rank 0 only, src/imc_state.h:283-287)
+    total_transport_time += max_transport_time;
   }
 
   // src/imc_state.h:292-296

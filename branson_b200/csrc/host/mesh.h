@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <iomanip>
 #include <iostream>
+#include <stdexcept>
 #include <vector>
 
 #include "comm.h"
@@ -234,33 +235,50 @@ public:
       total_abs_E += abs_E[i];
       total_post_mat_E += mat_E_scratch[i];
     }
-    if (verbose_print && rank == 0) {
-      using std::setw;
-      std::cout.precision(8);
-      std::cout << "-------- VERBOSE PRINT BLOCK: CELL TEMPERATURE --------" << std::endl;
-      std::cout << std::right << setw(12) << "cell" << " " << setw(12) << "T_e" << " " << setw(12) << "T_r" << " "
-                << setw(12) << "abs_E" << " " << std::endl;
-      for (uint32_t i = 0; i < n_cell; ++i)
-        std::cout << std::right << setw(12) << i << " " << setw(12) << T_e[i] << " " << setw(12) << T_r[i] << " "
-                  << setw(12) << abs_E[i] << " " << std::endl;
-      std::cout << "-------------------------------------------------------" << std::endl;
-    }
+    print_verbose_block(abs_E);
     abs_E.assign(abs_E.size(), 0.0);
     track_E.assign(track_E.size(), 0.0);
     imc_state.set_absorbed_E(total_abs_E);
     imc_state.set_post_mat_E(total_post_mat_E);
   }
 
+  // the reference's per-cycle temperature dump (src/mesh.h:364-381), deck option <print_verbose>
+  bool get_verbose_print() const { return verbose_print; }
+  void print_verbose_block(const std::vector<double> &abs_E) const {
+    if (!verbose_print || rank != 0) return;
+    using std::setw;
+    std::cout.precision(8);
+    std::cout << "-------- VERBOSE PRINT BLOCK: CELL TEMPERATURE --------" << std::endl;
+    std::cout << std::right << setw(12) << "cell" << " " << setw(12) << "T_e" << " " << setw(12) << "T_r" << " "
+              << setw(12) << "abs_E" << " " << std::endl;
+    for (uint32_t i = 0; i < n_cell; ++i)
+      std::cout << std::right << setw(12) << i << " " << setw(12) << T_e[i] << " " << setw(12) << T_r[i] << " "
+                << setw(12) << abs_E[i] << " " << std::endl;
+    std::cout << "-------------------------------------------------------" << std::endl;
+  }
+
+  // Device-mesh runs (Driver_Options::mesh_on_device): the cell state lives in HBM and this object's T_e / T_r / f / op /
+  // E arrays stop being updated.  The driver marks the mesh, after which the state getters throw instead of handing out
+  // stale values, unless the driver has mirrored the device arrays back for this cycle (mirror_from_device).
+  void set_device_resident() { device_resident = true; state_current = false; }
+  bool is_device_resident() const { return device_resident; }
+  void mirror_from_device(const std::vector<double> &T_e_dev, const std::vector<double> &T_r_dev) {
+    T_e = T_e_dev;
+    T_r = T_r_dev;
+    state_current = true;
+  }
+  void invalidate_mirror() { state_current = false; }
+
   // ---- what the sourcing / device side reads ----
-  const std::vector<double> &get_census_E() const { return m_census_E; }
-  const std::vector<double> &get_emission_E() const { return m_emission_E; }
-  const std::vector<double> &get_source_E() const { return m_source_E; }
+  const std::vector<double> &get_census_E() const { need_host_state(false); return m_census_E; }
+  const std::vector<double> &get_emission_E() const { need_host_state(false); return m_emission_E; }
+  const std::vector<double> &get_source_E() const { need_host_state(false); return m_source_E; }
   double get_total_photon_E() const { return total_photon_E; }
-  const std::vector<double> &get_f() const { return f; }
-  const std::vector<double> &get_op_a() const { return op_a; }
-  const std::vector<double> &get_op_s() const { return op_s; }
-  const std::vector<double> &get_T_e() const { return T_e; }
-  const std::vector<double> &get_T_r() const { return T_r; }
+  const std::vector<double> &get_f() const { need_host_state(false); return f; }
+  const std::vector<double> &get_op_a() const { need_host_state(false); return op_a; }
+  const std::vector<double> &get_op_s() const { need_host_state(false); return op_s; }
+  const std::vector<double> &get_T_e() const { need_host_state(true); return T_e; }
+  const std::vector<double> &get_T_r() const { need_host_state(true); return T_r; }
   const std::vector<double> &get_T_s() const { return T_s; }
   const std::vector<Region> &get_regions() const { return regions; }
   const std::vector<uint32_t> &get_region_index() const { return region_index; }
@@ -270,6 +288,11 @@ public:
   int get_n_ranks() const { return n_ranks; }
 
 private:
+  void need_host_state(bool mirrored_ok) const {
+    if (device_resident && !(mirrored_ok && state_current))
+      throw std::logic_error("Mesh: the cell state lives on the device in this run (mesh_on_device); read it through "
+                             "Replicated_Driver::device_array / bhost_get_array");
+  }
   template <class Start, class Delta, class Count>
   static void build_axis(uint32_t n_div, Start start, Delta delta, Count count, std::vector<double> &faces,
                          std::vector<uint32_t> &div_of) {
@@ -292,6 +315,7 @@ private:
   uint32_t ngx, ngy, ngz, n_global, n_cell;
   int rank, n_ranks;
   bool verbose_print, replicated = false;
+  bool device_resident = false, state_current = false;
   const Comm &comm;
   double total_photon_E = 0.0, replicated_factor = 1.0;
   std::vector<Region> regions;

@@ -11,6 +11,7 @@
 //   mesh.update_temperature                 (:96)   host
 //   rank != 0 zeroes its material sums, print_conservation, next_time_step (:100-120)
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -73,7 +74,9 @@ inline void replicated_transport(const Mesh &mesh, const GPU_Setup &gpu_setup, I
   rep.t_transport = t1 - t0;
   // abs_E / track_E: summed over ranks on the device (NVLink), then handed to the host once
   if (!comm.single()) {
-    if (comm.has_device_allreduce()) {
+    if (comm.has_native()) {
+      gpu_setup.check(bgpu_comm_allreduce_tallies(ctx, nullptr, nullptr), "bgpu_comm_allreduce_tallies");
+    } else if (comm.has_device_allreduce()) {
       void *dptr = nullptr;
       uint64_t n = 0;
       gpu_setup.check(bgpu_tally_buffer(ctx, 0, &dptr, &n), "bgpu_tally_buffer");
@@ -112,6 +115,7 @@ public:
                                      mesh.get_region_index().data(), mesh.get_T_e().data(), mesh.get_T_r0().data(),
                                      mesh.get_T_s().data()),
                       "bgpu_mesh_init");
+      mesh.set_device_resident();
     }
   }
 
@@ -126,10 +130,18 @@ public:
     return v;
   }
 
-  // one trip of the reference's while loop with the mesh physics on the device
+  // One trip of the reference's while loop (src/replicated_driver.h:47-121) with the mesh physics on the device.
+  // Multi-rank runs make ONE collective per cycle (csrc/comm_native.cuh): the source-energy sums of :56-59 and
+  // src/mesh.h:291-294 are formed locally for every rank (all ranks hold the same cell state), and the tallies travel
+  // together with every rank's conservation scalars in one packed in-place all-reduce that update_temperature consumes
+  // on the stream -- one host synchronisation after transport.
+  enum : int { RS_EMISSION = 0, RS_SOURCE, RS_PRE_CENSUS, RS_POST_CENSUS, RS_EXIT, RS_TRANSPORT_TIME, RS_TRANS_PARTICLES,
+               RS_CENSUS_SIZE, RS_NEW_PHOTON_E, RS_USED };
+  static_assert(RS_USED <= BGPU_RANK_SCALARS, "rank scalars exceed the tail row");
+
   Cycle_Report cycle_device_mesh() {
     Cycle_Report rep{};
-    const int rank = comm.get_rank();
+    const int rank = comm.get_rank(), n_ranks = comm.get_n_rank();
     const double t_begin = wall_now();
     rep.step = imc_state.get_step();
     rep.dt = imc_state.get_dt();
@@ -137,22 +149,24 @@ public:
     rep.next_dt = imc_state.get_next_dt();
     if (rank == 0 && opt.print) imc_state.print_timestep_header();
     bgpu_ctx *ctx = gpu_setup.get_ctx();
+    if (n_ranks > 1 && !comm.has_native())
+      throw GPU_Error("mesh_on_device needs the native communicator (bgpu_comm_init_rank / bgpu_comm_init_local) in "
+                      "multi-rank runs");
+    mesh.invalidate_mirror();
 
-    // mesh.calculate_photon_energy (src/replicated_driver.h:53)
-    bgpu_mesh_sums sums{};
-    gpu_setup.check(bgpu_mesh_calculate_photon_energy(ctx, imc_state.get_dt(), imc_state.get_step(), &sums),
-                    "bgpu_mesh_calculate_photon_energy");
-    if (!comm.single()) {
-      double global_source_E{sums.emission_E + sums.census_E + sums.source_E};  // src/mesh.h:291-294
-      comm.sum(&global_source_E, 1);
-      gpu_setup.check(bgpu_mesh_redistribute(ctx, global_source_E, &sums), "bgpu_mesh_redistribute");
-    }
-    imc_state.set_pre_mat_E(sums.pre_mat_E);
-    imc_state.set_emission_E(sums.emission_E);
-    imc_state.set_source_E(sums.source_E);
-    if (imc_state.get_step() == 1) imc_state.set_pre_census_E(sums.census_E);
-    double global_source_energy = sums.total_photon_E;
-    comm.sum(&global_source_energy, 1);
+    // mesh.calculate_photon_energy (src/replicated_driver.h:53) incl. the replicated redistribution, every rank's totals
+    rank_sums.assign((size_t)n_ranks, bgpu_mesh_sums{});
+    gpu_setup.check(bgpu_mesh_calculate_photon_energy_replicated(ctx, imc_state.get_dt(), imc_state.get_step(),
+                                                                 rank_sums.data()),
+                    "bgpu_mesh_calculate_photon_energy_replicated");
+    const bgpu_mesh_sums &mine = rank_sums[(size_t)rank];
+    imc_state.set_pre_mat_E(mine.pre_mat_E);
+    imc_state.set_emission_E(mine.emission_E);
+    imc_state.set_source_E(mine.source_E);
+    if (imc_state.get_step() == 1) imc_state.set_pre_census_E(mine.census_E);
+    // global source energy (src/replicated_driver.h:56-59): the ranks' totals summed in rank order
+    double global_source_energy = rank_sums[0].total_photon_E;
+    for (int r = 1; r < n_ranks; ++r) global_source_energy += rank_sums[(size_t)r].total_photon_E;
     rep.global_source_energy = global_source_energy;
     const double t1 = wall_now();
     rep.t_calc_energy = t1 - t_begin;
@@ -168,48 +182,65 @@ public:
     if (rank == 0 && opt.print) std::cout << "source time: " << rep.t_source << std::endl;
     imc_state.set_transported_particles(n_total);
 
-    comm.barrier();
-    const double t4 = wall_now();
     gpu_setup.check(bgpu_transport(ctx, imc_state.get_next_dt(),
                                    imc_p.get_transport_algorithm() == Constants::EVENT ? BGPU_EVENT : BGPU_HISTORY,
                                    opt.tally_mode),
                     "bgpu_transport");
     const double t5 = wall_now();
-    rep.t_transport = t5 - t4;
-    if (!comm.single()) {
-      if (!comm.has_device_allreduce())
-        throw GPU_Error("mesh_on_device needs a device all-reduce (NCCL) for the tallies in multi-rank runs");
-      void *dptr = nullptr;
-      uint64_t n = 0;
-      gpu_setup.check(bgpu_tally_buffer(ctx, 0, &dptr, &n), "bgpu_tally_buffer");
-      comm.sum_device(dptr, n, bgpu_stream(ctx));
-    }
-    const double t6 = wall_now();
-    rep.t_allreduce = t6 - t5;
+    rep.t_transport = t5 - t3;
     gpu_setup.check(bgpu_get_tallies(ctx, nullptr, nullptr, &rep.gpu), "bgpu_get_tallies");
     imc_state.set_exit_E(rep.gpu.exit_E);
     imc_state.set_post_census_E(rep.gpu.census_E);
     imc_state.set_census_size(rep.gpu.n_census);
     imc_state.set_rank_transport_runtime(rep.t_transport);
 
-    // mesh.update_temperature (src/replicated_driver.h:96)
-    gpu_setup.check(bgpu_mesh_update_temperature(ctx, &sums), "bgpu_mesh_update_temperature");
+    // the cycle's one collective + mesh.update_temperature (src/replicated_driver.h:91-96)
+    double mine_s[BGPU_RANK_SCALARS] = {};
+    mine_s[RS_EMISSION] = mine.emission_E;
+    mine_s[RS_SOURCE] = mine.source_E;
+    mine_s[RS_PRE_CENSUS] = st.pre_census_E;
+    mine_s[RS_POST_CENSUS] = rep.gpu.census_E;
+    mine_s[RS_EXIT] = rep.gpu.exit_E;
+    mine_s[RS_TRANSPORT_TIME] = rep.t_transport;
+    mine_s[RS_TRANS_PARTICLES] = (double)n_total;
+    mine_s[RS_CENSUS_SIZE] = (double)rep.gpu.n_census;
+    mine_s[RS_NEW_PHOTON_E] = st.new_photon_E;
+    all_scalars.assign((size_t)n_ranks * BGPU_RANK_SCALARS, 0.0);
+    bgpu_mesh_sums sums{};
+    gpu_setup.check(bgpu_mesh_finish_cycle(ctx, mine_s, all_scalars.data(), &sums), "bgpu_mesh_finish_cycle");
     imc_state.set_absorbed_E(sums.absorbed_E);
     imc_state.set_post_mat_E(sums.post_mat_E);
-    {
-      double rank_part = rep.gpu.census_E + rep.gpu.exit_E - rep.gpu.pre_census_E - st.new_photon_E;
-      comm.sum(&rank_part, 1);
-      rep.rad_balance_exact = sums.absorbed_E + rank_part;  // absorbed_E is a tree sum here (mesh_dev.cuh)
-    }
-    rep.t_update_T = wall_now() - t6;
+    rep.t_update_T = wall_now() - t5;
 
-    comm.barrier();
+    // IMC_State::print_conservation (src/imc_state.h:207-252) from every rank's scalars, summed in rank order; the
+    // material sums are rank 0's alone (src/replicated_driver.h:100-104) -- every rank holds the same values
+    auto col = [&](int r, int k) { return all_scalars[(size_t)r * BGPU_RANK_SCALARS + k]; };
+    double d[8] = {sums.absorbed_E, 0.0, 0.0, 0.0, mine.pre_mat_E, 0.0, sums.post_mat_E, 0.0};
+    double trans = 0.0, census = 0.0, tmax = col(0, RS_TRANSPORT_TIME), tmin = tmax, rank_parts = 0.0;
+    for (int r = 0; r < n_ranks; ++r) {
+      d[1] += col(r, RS_EMISSION);
+      d[2] += col(r, RS_SOURCE);
+      d[3] += col(r, RS_PRE_CENSUS);
+      d[5] += col(r, RS_POST_CENSUS);
+      d[7] += col(r, RS_EXIT);
+      trans += col(r, RS_TRANS_PARTICLES);
+      census += col(r, RS_CENSUS_SIZE);
+      tmax = std::max(tmax, col(r, RS_TRANSPORT_TIME));
+      tmin = std::min(tmin, col(r, RS_TRANSPORT_TIME));
+      rank_parts += col(r, RS_POST_CENSUS) + col(r, RS_EXIT) - col(r, RS_PRE_CENSUS) - col(r, RS_NEW_PHOTON_E);
+    }
+    rep.rad_balance_exact = sums.absorbed_E + rank_parts;  // absorbed_E is a tree sum here (mesh_dev.cuh)
     if (rank) {  // for replicated, just let root do conservation (:100-104)
       imc_state.set_absorbed_E(0.0);
       imc_state.set_pre_mat_E(0.0);
       imc_state.set_post_mat_E(0.0);
     }
-    imc_state.print_conservation(comm, opt.print);
+    imc_state.set_global_sums(d, (uint64_t)trans, (uint64_t)census, tmax, tmin);
+    imc_state.finish_conservation(opt.print);
+    if (mesh.get_verbose_print()) {  // the reference's per-cycle temperature dump (src/mesh.h:364-381)
+      mesh.mirror_from_device(device_array("T_e"), device_array("T_r"));
+      mesh.print_verbose_block(device_array("abs_E"));
+    }
     comb_census(rep);
     imc_state.next_time_step();
     rep.t_cycle = wall_now() - t_begin;
@@ -333,6 +364,8 @@ private:
   GPU_Setup &gpu_setup;
   Driver_Options opt;
   std::vector<double> abs_E, track_E, last_abs_E, last_track_E;
+  std::vector<bgpu_mesh_sums> rank_sums;
+  std::vector<double> all_scalars;
   std::map<std::string, std::vector<double>> dev_cache;
 };
 

@@ -163,20 +163,42 @@ __global__ void __launch_bounds__(MESH_TILE_THREADS) k_mesh_energy(const MeshPhy
 // recomputed.  Also forms what the reference's Allreduce of m_emission_E (:343-345) yields, locally: every rank holds
 // the same pre-redistribution share and takes the same decision, so the rank-ordered sum is either the share added
 // n_ranks times or the one un-split value (see host/mesh.h).
-__global__ void __launch_bounds__(MESH_TILE_THREADS) k_mesh_redistribute(const MeshPhysParams P) {
+//
+// No collective is needed for any of it.  The global source energy the rule divides by (:291-294) is the rank-ordered
+// sum of n_ranks identical totals and is read from `sums_in` (k_mesh_final_sums wrote this rank's totals there); and
+// because every rank takes the same decisions from the same values, this rank forms the post-redistribution totals of
+// EVERY rank (tile_sums[r][q][tile]) -- what the reference gets from its second MPI_Allreduce of total_photon_E
+// (src/replicated_driver.h:56-59) is then a local rank-ordered sum (k_mesh_final_sums).  Only this rank's energies are
+// written back.
+__global__ void __launch_bounds__(MESH_TILE_THREADS) k_mesh_redistribute(const MeshPhysParams P,
+                                                                         const double *__restrict__ sums_in) {
   __shared__ double s_red[MESH_TILE_THREADS >> 5];
   const uint32_t nc = P.mesh.n_cells;
   const uint32_t base = blockIdx.x * MESH_TILE + threadIdx.x * MESH_TILE_ITEMS;
-  double s_em = 0.0, s_cen = 0.0, s_src = 0.0, s_tot = 0.0;
-#pragma unroll 1
+  // src/mesh.h:291-294: global_source_E = Allreduce(tot_emission + tot_census + tot_source), summed in rank order
+  double gse;
+  if (sums_in) {
+    const double t = sums_in[MS_EMISSION] + sums_in[MS_CENSUS] + sums_in[MS_SOURCE];
+    gse = t;
+    for (int r = 1; r < P.n_ranks; ++r) gse += t;
+  } else {
+    gse = P.global_source_E;
+  }
+  double em0[MESH_TILE_ITEMS], cen0[MESH_TILE_ITEMS], src0[MESH_TILE_ITEMS];
+  bool em_small[MESH_TILE_ITEMS], cen_small[MESH_TILE_ITEMS], src_small[MESH_TILE_ITEMS];
+#pragma unroll
   for (int it = 0; it < MESH_TILE_ITEMS; ++it) {
     const uint32_t i = base + it;
-    if (i >= nc) break;
-    const bool mine = (int)(i % (uint32_t)P.n_ranks) == P.rank;
-    double em = P.E_emission[i], cen = P.E_census[i], src = P.E_source[i];
-    const bool em_small = em > 0.0 && int(P.n_user * (em / P.global_source_E)) == 0;
+    em0[it] = cen0[it] = src0[it] = 0.0;
+    em_small[it] = cen_small[it] = src_small[it] = false;
+    if (i >= nc) continue;
+    const double em = P.E_emission[i], cen = P.E_census[i], src = P.E_source[i];
+    em0[it] = em; cen0[it] = cen; src0[it] = src;
+    em_small[it] = em > 0.0 && int(P.n_user * (em / gse)) == 0;
+    cen_small[it] = P.step == 1 && cen > 0.0 && int(P.n_user * (cen / gse)) == 0;
+    src_small[it] = src > 0.0 && int(P.n_user * (src / gse)) == 0;
     double g;
-    if (em_small) {
+    if (em_small[it]) {
       g = em / P.replicated_factor;
       for (int r = 1; r < P.n_ranks; ++r) g = g + 0.0;
     } else {
@@ -184,23 +206,35 @@ __global__ void __launch_bounds__(MESH_TILE_THREADS) k_mesh_redistribute(const M
       for (int r = 1; r < P.n_ranks; ++r) g = g + em;
     }
     P.E_emission_global[i] = g;
-    if (P.step == 1 && cen > 0.0 && int(P.n_user * (cen / P.global_source_E)) == 0)
-      cen = mine ? cen / P.replicated_factor : 0.0;
-    if (em_small) em = mine ? em / P.replicated_factor : 0.0;
-    if (src > 0.0 && int(P.n_user * (src / P.global_source_E)) == 0) src = mine ? src / P.replicated_factor : 0.0;
-    P.E_emission[i] = em;
-    P.E_census[i] = cen;
-    P.E_source[i] = src;
-    s_em += em;
-    s_cen += cen;
-    s_src += src;
-    s_tot += src + cen + em;
   }
   const uint32_t nt = P.n_tiles;
-  tile_store(s_em, s_red, &P.tile_sums[MS_EMISSION * nt + blockIdx.x]);
-  tile_store(s_cen, s_red, &P.tile_sums[MS_CENSUS * nt + blockIdx.x]);
-  tile_store(s_src, s_red, &P.tile_sums[MS_SOURCE * nt + blockIdx.x]);
-  tile_store(s_tot, s_red, &P.tile_sums[MS_TOTAL * nt + blockIdx.x]);
+#pragma unroll 1
+  for (int r = 0; r < P.n_ranks; ++r) {
+    double s_em = 0.0, s_cen = 0.0, s_src = 0.0, s_tot = 0.0;
+#pragma unroll
+    for (int it = 0; it < MESH_TILE_ITEMS; ++it) {
+      const uint32_t i = base + it;
+      if (i >= nc) continue;
+      const bool owner = (int)(i % (uint32_t)P.n_ranks) == r;
+      const double em = em_small[it] ? (owner ? em0[it] / P.replicated_factor : 0.0) : em0[it];
+      const double cen = cen_small[it] ? (owner ? cen0[it] / P.replicated_factor : 0.0) : cen0[it];
+      const double src = src_small[it] ? (owner ? src0[it] / P.replicated_factor : 0.0) : src0[it];
+      if (r == P.rank) {
+        P.E_emission[i] = em;
+        P.E_census[i] = cen;
+        P.E_source[i] = src;
+      }
+      s_em += em;
+      s_cen += cen;
+      s_src += src;
+      s_tot += src + cen + em;
+    }
+    double *ts = P.tile_sums + (uint64_t)r * MS_N * nt;
+    tile_store(s_em, s_red, &ts[MS_EMISSION * nt + blockIdx.x]);
+    tile_store(s_cen, s_red, &ts[MS_CENSUS * nt + blockIdx.x]);
+    tile_store(s_src, s_red, &ts[MS_SOURCE * nt + blockIdx.x]);
+    tile_store(s_tot, s_red, &ts[MS_TOTAL * nt + blockIdx.x]);
+  }
 }
 
 // src/mesh.h:343-362: new material temperature from the (rank-summed) tallies, radiation temperature diagnostic,
@@ -231,15 +265,16 @@ __global__ void __launch_bounds__(MESH_TILE_THREADS) k_mesh_update_temperature(c
   tile_store(s_mat, s_red, &P.tile_sums[MS_POST_MAT * nt + blockIdx.x]);
 }
 
-// the tiles in order, one thread per quantity: out[q] = sum_t tile_sums[q][t]
+// the tiles in order, one thread per quantity and rank block: out[r][q] = sum_t tile_sums[r][q][t]
+// (blockIdx.x = r; the kernels that are not per-rank use block 0 = the rank's own block)
 __global__ void k_mesh_final_sums(const double *__restrict__ tile_sums, uint32_t n_tiles, uint32_t q_mask,
                                   double *__restrict__ out) {
   const uint32_t q = threadIdx.x;
   if (q >= MS_N || !((q_mask >> q) & 1u)) return;
-  const double *v = tile_sums + (uint64_t)q * n_tiles;
+  const double *v = tile_sums + ((uint64_t)blockIdx.x * MS_N + q) * n_tiles;
   double s = 0.0;
   for (uint32_t t = 0; t < n_tiles; ++t) s += v[t];
-  out[q] = s;
+  out[blockIdx.x * MS_N + q] = s;
 }
 
 }  // namespace bg

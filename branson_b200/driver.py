@@ -1,8 +1,10 @@
 """ctypes binding of libbranson_host.so (include/branson_host.h): the C++ host layer -- Input, IMC_Parameters,
 IMC_State, Mesh and the replicated cycle driver -- stepped one cycle at a time.
 
-Harness plumbing only.  Multi-GPU: one process per GPU (torchrun); `TorchComm` hands torch.distributed collectives to
-the C++ driver, the tally all-reduce runs in place on the device buffer over NCCL / NVLink.
+Harness plumbing only.  Multi-GPU: one process per GPU (torchrun).  The collectives of the cycle are native
+(csrc/comm_native.cuh: ncclAllReduce on the ctx stream, called from C++); Python only carries the NCCL unique id from
+rank 0 to the other processes (`init_nccl`), or groups several in-process ranks (`init_local`: one thread per rank).
+`TorchComm` (gloo callbacks) remains for the CPU-only tests of the host-side rank partitioning.
 """
 from __future__ import annotations
 
@@ -17,7 +19,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(gpu.LIB_DIR, "libbranson_host.so")
 
 EXPORTS = ["bhost_create", "bhost_destroy", "bhost_last_error", "bhost_finished", "bhost_calculate_photon_energy",
-           "bhost_cycle", "bhost_next_time_step", "bhost_get_array", "bhost_get_param", "bhost_gpu_ctx", "bhost_total_transport_time"]
+           "bhost_cycle", "bhost_next_time_step", "bhost_get_array", "bhost_get_param", "bhost_gpu_ctx", "bhost_total_transport_time",
+           "bhost_comm_unique_id", "bhost_comm_init_rank", "bhost_comm_init_local"]
+COMM_ID_BYTES = 128
 
 _F_SUM = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_uint64)
 _F_SUMDEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
@@ -86,6 +90,9 @@ def lib():
         L.bhost_gpu_ctx.restype = vp
         L.bhost_total_transport_time.argtypes = [vp]
         L.bhost_total_transport_time.restype = C.c_double
+        L.bhost_comm_unique_id.argtypes = [C.c_char_p]
+        L.bhost_comm_init_rank.argtypes = [vp, C.c_char_p]
+        L.bhost_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
         _LIB = L
     return _LIB
 
@@ -95,67 +102,101 @@ class HostError(RuntimeError):
 
 
 class TorchComm:
-    """torch.distributed collectives for the C++ driver (csrc/host/comm.h).  Host scalars travel through a small
-    tensor on `device` (cuda:N with NCCL, cpu with gloo); the tally buffer is all-reduced in place on the GPU."""
+    """torch.distributed (gloo) collectives as comm.h callbacks, for host-only drivers (`no_gpu=True`): the CPU tests
+    of the rank partitioning.  GPU runs do not use it: their collectives are native (init_nccl / init_local)."""
 
-    def __init__(self, device):
+    def __init__(self, device="cpu"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.device = torch.device(device)
+        if self.device.type != "cpu":
+            raise ValueError("TorchComm carries host scalars of CPU-only runs; GPU ranks use driver.init_nccl")
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.device_allreduce_bytes = 0
-        self._cbs = [_F_SUM(self._sum), _F_SUMDEV(self._sum_dev), _F_SUMU(self._sum_u64), _F_SUM(self._max),
-                     _F_SUM(self._min), _F_BAR(self._barrier)]
-        null_dev = C.cast(None, _F_SUMDEV)
-        self.struct = CommStruct(None, self._cbs[0], self._cbs[1] if self.device.type == "cuda" else null_dev,
-                                 self._cbs[2], self._cbs[3], self._cbs[4], self._cbs[5])
+        self._cbs = [_F_SUM(self._sum), _F_SUMU(self._sum_u64), _F_SUM(self._max), _F_SUM(self._min),
+                     _F_BAR(self._barrier)]
+        self.struct = CommStruct(None, self._cbs[0], C.cast(None, _F_SUMDEV), self._cbs[1], self._cbs[2],
+                                 self._cbs[3], self._cbs[4])
 
-    def _host_reduce(self, buf, n, dtype, np_dtype, op):
+    def _host_reduce(self, buf, n, np_dtype, op):
         try:
             a = np.ctypeslib.as_array(buf, shape=(n,))
-            t = self.torch.from_numpy(a.astype(np_dtype, copy=True)).to(self.device)
+            t = self.torch.from_numpy(a.astype(np_dtype, copy=True))
             self.dist.all_reduce(t, op=op)
-            a[:] = t.cpu().numpy().astype(a.dtype)
+            a[:] = t.numpy().astype(a.dtype)
             return 0
         except Exception as e:  # pragma: no cover
             print(f"TorchComm: {e}", flush=True)
             return 1
 
     def _sum(self, _u, buf, n):
-        return self._host_reduce(buf, n, None, np.float64, self.dist.ReduceOp.SUM)
+        return self._host_reduce(buf, n, np.float64, self.dist.ReduceOp.SUM)
 
     def _max(self, _u, buf, n):
-        return self._host_reduce(buf, n, None, np.float64, self.dist.ReduceOp.MAX)
+        return self._host_reduce(buf, n, np.float64, self.dist.ReduceOp.MAX)
 
     def _min(self, _u, buf, n):
-        return self._host_reduce(buf, n, None, np.float64, self.dist.ReduceOp.MIN)
+        return self._host_reduce(buf, n, np.float64, self.dist.ReduceOp.MIN)
 
     def _sum_u64(self, _u, buf, n):
         # counts stay far below 2^63: carried as int64
-        return self._host_reduce(buf, n, None, np.int64, self.dist.ReduceOp.SUM)
-
-    def _sum_dev(self, _u, dptr, n, _stream):
-        try:
-            t = device_tensor_f64(self.torch, dptr, n, self.device)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-            self.torch.cuda.synchronize(self.device)
-            self.device_allreduce_bytes += 8 * n
-            return 0
-        except Exception as e:  # pragma: no cover
-            print(f"TorchComm device all-reduce: {e}", flush=True)
-            return 1
+        return self._host_reduce(buf, n, np.int64, self.dist.ReduceOp.SUM)
 
     def _barrier(self, _u):
         try:
-            if self.device.type == "cuda":
-                self.dist.barrier(device_ids=[self.device.index])
-            else:
-                self.dist.barrier()
+            self.dist.barrier()
             return 0
         except Exception as e:  # pragma: no cover
             print(f"TorchComm barrier: {e}", flush=True)
             return 1
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 of a multi-process run)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if lib().bhost_comm_unique_id(buf):
+        raise HostError("bhost_comm_unique_id: " + gpu.last_create_error())
+    return buf.raw
+
+
+def init_nccl(drv: "Driver", dist) -> None:
+    """Multi-process bootstrap: rank 0's NCCL unique id travels through torch.distributed's store (any backend), every
+    rank then creates its communicator natively (ncclCommInitRank on the driver's device context).  From here on the
+    cycle's collectives never touch Python."""
+    box = [comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    drv.comm_init_rank(box[0])
+
+
+def init_local(drivers) -> None:
+    """All ranks in this process (drivers[r] = rank r; step each from its own thread): NCCL when every rank has its own
+    GPU, the in-process rank-ordered device sum when they share one."""
+    arr = (C.c_void_p * len(drivers))(*[d._h for d in drivers])
+    if lib().bhost_comm_init_local(arr, len(drivers)):
+        raise HostError("bhost_comm_init_local: " + lib().bhost_last_error(drivers[0]._h).decode())
+
+
+def run_ranks(drivers, fn):
+    """fn(rank, driver) on one thread per in-process rank (the collectives rendezvous across the threads; ctypes calls
+    release the GIL); returns the list of results, re-raising the first failure."""
+    import threading
+    out, errs = [None] * len(drivers), [None] * len(drivers)
+
+    def work(r):
+        try:
+            out[r] = fn(r, drivers[r])
+        except BaseException as e:  # noqa: BLE001 -- re-raised below
+            errs[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(len(drivers))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return out
 
 
 def device_tensor_f64(torch, dptr: int, n: int, device):
@@ -196,6 +237,12 @@ class Driver:
             self.close()
         except Exception:
             pass
+
+    def comm_init_rank(self, unique_id: bytes):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        if lib().bhost_comm_init_rank(self._h, unique_id):
+            raise HostError(lib().bhost_last_error(self._h).decode())
 
     def finished(self) -> bool:
         return bool(lib().bhost_finished(self._h))

@@ -64,8 +64,11 @@ EXPORTS = [
     "bgpu_stream", "bgpu_device", "bgpu_transport_photons_aos", "bgpu_upload_photons", "bgpu_download_photons",
     "bgpu_list_size", "bgpu_enable_counters", "bgpu_set_launch", "bgpu_set_divergence", "bgpu_census_energy", "bgpu_comb_census", "bgpu_sort_census_by_cell", "bgpu_set_tally_copies", "bgpu_set_event_tail", "bgpu_set_group_walk", "bgpu_test_rng_draws", "bgpu_test_threefry", "bgpu_test_fastmath",
     "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
-    "bgpu_mesh_update_temperature", "bgpu_mesh_get",
+    "bgpu_mesh_update_temperature", "bgpu_mesh_get", "bgpu_mesh_calculate_photon_energy_replicated",
+    "bgpu_mesh_finish_cycle", "bgpu_comm_unique_id", "bgpu_comm_init_rank", "bgpu_comm_init_local", "bgpu_comm_info",
+    "bgpu_comm_allreduce_host", "bgpu_comm_allreduce_tallies",
 ]
+COMM_NONE, COMM_NCCL, COMM_LOCAL = 0, 1, 2
 
 
 def lib():
@@ -109,6 +112,10 @@ def lib():
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
         L.bgpu_test_threefry.argtypes = [vp, vp]
         L.bgpu_test_fastmath.argtypes = [C.c_int, u64, vp, vp, vp]
+        L.bgpu_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64)]
+        L.bgpu_comm_init_local.argtypes = [C.POINTER(vp), i32]
+        L.bgpu_comm_allreduce_tallies.argtypes = [vp, vp, vp]
+        L.bgpu_comm_allreduce_host.argtypes = [vp, vp, u64, i32]
         _LIB = L
     return _LIB
 
@@ -123,6 +130,17 @@ def _f64(a):
 
 class GpuError(RuntimeError):
     pass
+
+
+def last_create_error() -> str:
+    return (lib().bgpu_last_error(None) or b"").decode()
+
+
+def comm_info(handle) -> dict:
+    """back end (COMM_NONE / COMM_NCCL / COMM_LOCAL), number of collectives and bytes reduced through a ctx so far"""
+    k, n, b = C.c_int(), C.c_uint64(), C.c_uint64()
+    lib().bgpu_comm_info(handle, C.byref(k), C.byref(n), C.byref(b))
+    return {"kind": k.value, "calls": n.value, "bytes": b.value}
 
 
 def faces_from_nodes(nodes: np.ndarray, nx: int, ny: int, nz: int):

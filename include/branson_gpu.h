@@ -160,6 +160,36 @@ int bgpu_get_tallies(bgpu_ctx *ctx, double *abs_E, double *track_E, bgpu_cycle_s
  * src/replicated_driver.h:91-94): n_doubles doubles = interleaved Cell_Tally {abs_E, track_E}[n_cells] followed by
  * `extra` caller-owned doubles.  The caller all-reduces it in place (NCCL) and then calls bgpu_get_tallies. */
 int bgpu_tally_buffer(bgpu_ctx *ctx, uint64_t extra, void **device_ptr, uint64_t *n_doubles);
+/* ---- replicated-mode collectives, native (csrc/comm_native.cuh) -----------------------------------------------------
+ * Replace the MPI calls of the reference's replicated cycle: MPI_Allreduce of abs_E / track_E
+ * (src/replicated_driver.h:91-94), of the source energies (src/replicated_driver.h:56-59, src/mesh.h:291-294), of
+ * m_emission_E (src/mesh.h:343-345) and the scalar reductions of IMC_State::print_conservation
+ * (src/imc_state.h:207-252).  A rank is a bgpu_ctx (bgpu_mesh_desc.rank / n_ranks).  Two back ends:
+ *   NCCL (one GPU per rank, NVLink / NVSwitch) -- several processes: rank 0 calls bgpu_comm_unique_id, the launcher
+ *     carries the 128 bytes to every process (torchrun store, a file, MPI_Bcast ...), every rank calls
+ *     bgpu_comm_init_rank; one process with a host thread per rank: bgpu_comm_init_local on the array of contexts;
+ *   in-process (bgpu_comm_init_local with all ranks on ONE device -- the reference maps rank % n_devices,
+ *     src/gpu_setup.h:68-78): the ranks' threads meet and one kernel forms the rank-ordered sum.
+ * libnccl.so.2 is loaded on first use; a single-rank run never touches it.  A collective call blocks the calling host
+ * thread only until every rank has made the same call (in-process back end) or not at all (NCCL): the reduction itself
+ * is ordered on the ctx stream. */
+#define BGPU_COMM_ID_BYTES 128
+enum { BGPU_COMM_NONE = 0, BGPU_COMM_NCCL = 1, BGPU_COMM_LOCAL = 2 };
+enum { BGPU_OP_SUM = 0, BGPU_OP_MAX = 1, BGPU_OP_MIN = 2 };
+int bgpu_comm_unique_id(char id[BGPU_COMM_ID_BYTES]);                 /* ncclGetUniqueId */
+int bgpu_comm_init_rank(bgpu_ctx *ctx, const char id[BGPU_COMM_ID_BYTES]); /* ncclCommInitRank(n_ranks, id, rank) */
+int bgpu_comm_init_local(bgpu_ctx **ctxs, int n_ranks);               /* ctxs[r] = rank r, all in this process */
+int bgpu_comm_info(const bgpu_ctx *ctx, int *kind, uint64_t *calls, uint64_t *bytes);
+/* in-place reduction of n HOST doubles over the ranks (staged through the device; the host-mesh path's scalars) */
+int bgpu_comm_allreduce_host(bgpu_ctx *ctx, double *buf, uint64_t n, int op);
+/* The cycle's ONE collective: the packed buffer {abs_E, track_E}[n_cells] + tail[n_ranks][BGPU_RANK_SCALARS] is summed
+ * in place over the ranks on the ctx stream.  Every rank contributes `rank_scalars` (BGPU_RANK_SCALARS doubles of the
+ * caller's choosing: census / exit energy, photon counts below 2^53, transport time ...) in its own row of the tail and
+ * zeros elsewhere, so that after the sum `all_scalars` [n_ranks][BGPU_RANK_SCALARS] holds every rank's values and sums,
+ * maxima and minima over ranks can be formed locally in rank order.  With one rank: a copy. */
+#define BGPU_RANK_SCALARS 12
+int bgpu_comm_allreduce_tallies(bgpu_ctx *ctx, const double *rank_scalars, double *all_scalars);
+
 /* cudaStreamSynchronize of the ctx stream / raw stream handle for collective plumbing */
 int bgpu_sync(bgpu_ctx *ctx);
 void *bgpu_stream(bgpu_ctx *ctx);
@@ -226,6 +256,16 @@ int bgpu_mesh_calculate_photon_energy(bgpu_ctx *ctx, double dt, uint32_t step, b
 /* src/mesh.h:291-315 (replicated runs with more than one rank): global_source_E is the all-reduced
  * emission + census + source total of bgpu_mesh_calculate_photon_energy; the four energy sums are recomputed */
 int bgpu_mesh_redistribute(bgpu_ctx *ctx, double global_source_E, bgpu_mesh_sums *sums);
+/* calculate_photon_energy + the replicated redistribution WITHOUT their collectives (src/mesh.h:291-294,
+ * src/replicated_driver.h:56-59): every rank holds the same cell state and takes the same decisions, so this rank forms
+ * the post-redistribution totals of every rank itself.  rank_sums [n_ranks]: rank r's emission / census / source /
+ * total_photon_E (pre_mat_E is the same for all); the caller's global source energy is their rank-ordered sum.  With
+ * one rank: bgpu_mesh_calculate_photon_energy. */
+int bgpu_mesh_calculate_photon_energy_replicated(bgpu_ctx *ctx, double dt, uint32_t step, bgpu_mesh_sums *rank_sums);
+/* End of a device-mesh cycle in one stream-ordered chain: bgpu_comm_allreduce_tallies -> update_temperature
+ * (src/mesh.h:343-362) on the reduced tallies -> one host synchronisation that brings back `all_scalars` and the
+ * absorbed / post-material energy sums. */
+int bgpu_mesh_finish_cycle(bgpu_ctx *ctx, const double *rank_scalars, double *all_scalars, bgpu_mesh_sums *sums);
 /* bgpu_source from the device-resident energies of this cycle */
 int bgpu_mesh_source(bgpu_ctx *ctx, uint32_t cycle, double total_E, uint64_t *n_new, uint64_t *n_total);
 /* src/mesh.h:343-362 from the tally buffer (all-reduced by the caller in multi-rank runs) */

@@ -68,6 +68,14 @@ typedef struct {
 bhost_driver *bhost_create(const char *xml_path, int rank, int n_ranks, const bhost_options *opt,
                            const bhost_comm *comm /* NULL: single rank */, char *err, size_t err_len);
 void bhost_destroy(bhost_driver *d);
+/* Multi-rank runs: the native communicator of the ranks' device contexts (bgpu_comm_*, include/branson_gpu.h) -- NCCL
+ * between GPUs, an in-process sum between ranks that share one.  Several processes (one per GPU): rank 0 calls
+ * bhost_comm_unique_id, the launcher carries the id to every process, every rank calls bhost_comm_init_rank.  One
+ * process holding all ranks (one host thread per rank steps its driver): bhost_comm_init_local(drivers, n_ranks).
+ * After either, bhost_cycle needs no `comm` callbacks. */
+int bhost_comm_unique_id(char id[BGPU_COMM_ID_BYTES]);
+int bhost_comm_init_rank(bhost_driver *d, const char id[BGPU_COMM_ID_BYTES]);
+int bhost_comm_init_local(bhost_driver **drivers, int n_ranks);
 const char *bhost_last_error(const bhost_driver *d);
 int bhost_finished(const bhost_driver *d);
 /* Mesh::calculate_photon_energy only (host; used by the CPU tests of the rank partitioning) */

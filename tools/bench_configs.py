@@ -57,9 +57,9 @@ def run_case_multi(name, deck, cycles, algorithm):
     rank, world, local = dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", "0"))
     tmp = tempfile.mkdtemp(prefix="bcfg_")
     xml = deck.write(os.path.join(tmp, f"{name}_{rank}.xml"))
-    comm = driver.TorchComm(f"cuda:{local}")
-    d = driver.Driver(xml, n_groups=deck.n_groups, rank=rank, n_ranks=world, device=local, algorithm=algorithm, comm=comm,
+    d = driver.Driver(xml, n_groups=deck.n_groups, rank=rank, n_ranks=world, device=local, algorithm=algorithm,
                       mesh_on_device=True)
+    driver.init_nccl(d, dist)  # the cycle's collective is native (csrc/comm_native.cuh)
     rows = []
     for c in range(cycles):
         torch.cuda.synchronize()
