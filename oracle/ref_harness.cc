@@ -11,6 +11,9 @@
 // config.h).  Output goes to oracle/_ref/ only.
 //
 // Usage: ref_harness <input.xml> <out_prefix> [max_cycles] [photon_dump_limit]
+//   REF_DUMP_LEVEL=1 (full-size parity runs): only the per-photon integers of the post-transport list (cell, group, RNG
+//   counter, descriptor), abs_E / T_e / T_r and the scalars are dumped -- no mesh tables, no pre-transport list, no
+//   per-photon doubles
 //   writes <out_prefix>.rank<r>.bin ; records are
 //   [u32 name_len][name][u8 dtype][u64 count][payload]
 //   dtype: 0=f64 1=u32 2=u64 3=u8
@@ -92,8 +95,27 @@ struct Dump {
 
 static_assert(sizeof(Photon) == 120, "reference Photon layout changed");
 
+int g_dump_level = 0;
+
 void dump_photons(Dump &d, const std::string &pfx, const std::vector<Photon> &p, size_t limit, bool post) {
   size_t n = std::min(p.size(), limit);
+  if (g_dump_level >= 1) {
+    if (!post) return;
+    std::vector<uint32_t> cell(n), group(n);
+    std::vector<uint8_t> desc(n);
+    std::vector<uint64_t> ctr(n);
+    for (size_t i = 0; i < n; ++i) {
+      cell[i] = p[i].m_cell_ID;
+      group[i] = p[i].group;
+      desc[i] = p[i].descriptors[0];
+      ctr[i] = p[i].m_rng.data[0];
+    }
+    d.u32(pfx + "cell", cell);
+    d.u32(pfx + "group", group);
+    d.u64(pfx + "ctr", ctr);
+    d.u8(pfx + "descriptor", desc);
+    return;
+  }
   std::vector<uint32_t> cell(n), group(n), stype(n);
   std::vector<uint8_t> desc(n);
   std::vector<uint64_t> ctr(n), stream(n);
@@ -142,6 +164,8 @@ int main(int argc, char **argv) {
   const std::string out_prefix(argv[2]);
   const uint32_t max_cycles = argc > 3 ? (uint32_t)std::atol(argv[3]) : 0xffffffffu;
   const size_t photon_limit = argc > 4 ? (size_t)std::atoll(argv[4]) : ~size_t(0);
+  if (const char *lv = std::getenv("REF_DUMP_LEVEL")) g_dump_level = std::atoi(lv);
+  const bool lean = g_dump_level >= 1;
   {
     const Info mpi_info;
     const int rank = mpi_info.get_rank();
@@ -169,7 +193,7 @@ int main(int argc, char **argv) {
     d.u64("n_groups", (uint64_t)BRANSON_N_GROUPS);
     d.u64("n_user_photons", imc_p.get_n_user_photons());
     d.u64("seed", imc_p.get_rng_seed());
-    {
+    if (!lean) {
       std::vector<double> nodes(6 * (size_t)n_cells);
       std::vector<uint32_t> region(n_cells), enext(6 * (size_t)n_cells), bc(6 * (size_t)n_cells);
       for (uint32_t i = 0; i < n_cells; ++i) {
@@ -203,7 +227,7 @@ int main(int argc, char **argv) {
       const std::string c = "c" + std::to_string(imc_state.get_step()) + "/";
       d.f64(c + "dt", imc_state.get_dt());
       d.f64(c + "time", imc_state.get_time());
-      {
+      if (!lean) {
         std::vector<double> Te(n_cells);
         for (uint32_t i = 0; i < n_cells; ++i) Te[i] = mesh.get_cell_ref(i).get_T_e();
         d.f64(c + "T_e_pre", Te);
@@ -213,7 +237,7 @@ int main(int argc, char **argv) {
       d.f64(c + "rank_total_photon_E", global_source_energy);
       MPI_Allreduce(MPI_IN_PLACE, &global_source_energy, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
       d.f64(c + "global_source_energy", global_source_energy);
-      {
+      if (!lean) {
         std::vector<double> f(n_cells), opa(n_cells), ops(n_cells);
         for (uint32_t i = 0; i < n_cells; ++i) {
           const Cell &cell = mesh.get_cell_ref(i);
@@ -260,8 +284,10 @@ int main(int argc, char **argv) {
       d.f64(c + "transport_seconds", imc_state.rank_transport_runtime);
       total_transport += imc_state.rank_transport_runtime;
       total_histories += all_photons.size();
-      d.f64(c + "rank_abs_E", abs_E);
-      d.f64(c + "rank_track_E", track_E);
+      if (!lean) {
+        d.f64(c + "rank_abs_E", abs_E);
+        d.f64(c + "rank_track_E", track_E);
+      }
 
       MPI_Allreduce(MPI_IN_PLACE, &abs_E[0], mesh.get_n_global_cells(), MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
       MPI_Allreduce(MPI_IN_PLACE, &track_E[0], mesh.get_n_global_cells(), MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);

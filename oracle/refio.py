@@ -49,8 +49,9 @@ def read_dump(path: str) -> dict:
 
 def run_reference(deck, n_ranks: int = 1, max_cycles: int | None = None, photon_limit: int | None = None,
                   workdir: str | None = None, timeout: float = 3600.0, comb_max: int | None = None,
-                  comb_stream: int = 0):
-    """Returns (list of per-rank dump dicts, stdout of rank 0)."""
+                  comb_stream: int = 0, dump_level: int = 0):
+    """Returns (list of per-rank dump dicts, stdout of rank 0).  dump_level 1: per-photon integers of the
+    post-transport list, abs_E / track_E / T_e / T_r and the scalars only (full-size runs)."""
     exe = harness_path(deck.n_groups)
     if not os.path.exists(exe):
         raise FileNotFoundError(f"{exe} (build with `make -C oracle ref` where /root/reference exists)")
@@ -59,6 +60,8 @@ def run_reference(deck, n_ranks: int = 1, max_cycles: int | None = None, photon_
     prefix = os.path.join(tmp, deck.name)
     env = dict(os.environ)
     env["BRANSON_SHIM_NRANKS"] = str(n_ranks)
+    if dump_level:
+        env["REF_DUMP_LEVEL"] = str(int(dump_level))
     if comb_max is not None:  # comb_photons on the final census (dumped under comb/...)
         env["REF_COMB_MAX"] = str(int(comb_max))
         env["REF_COMB_STREAM"] = str(int(comb_stream))

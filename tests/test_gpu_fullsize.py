@@ -1,6 +1,13 @@
-"""BASELINE-size runs on the GPU, checked through size-independent properties (the oracle would need minutes to
-hours here): exact photon bookkeeping, energy balance to 1e-12, deterministic-mode reproducibility against the atomic
-mode, and agreement of integer outcomes between work distributions."""
+"""BASELINE-size runs on the GPU.
+
+* photon by photon against the UNMODIFIED reference (oracle/_ref/ref_harness_g*, OpenMP on all host cores: its
+  per-photon integers do not depend on the thread count): 2 cycles of configs[2] at 1e7 photons and of big_cube 200^3 at
+  2e7 -- final cell, group, descriptor and RNG counter (= draws consumed, an exact proxy of the event sequence) of every
+  photon bit for bit, tallies and temperatures 1e-9;
+* size-independent properties: exact photon bookkeeping, energy balance to 1e-12, deterministic-mode reproducibility
+  against the atomic mode, and agreement of integer outcomes between work distributions."""
+import os
+
 import numpy as np
 import pytest
 
@@ -39,6 +46,56 @@ def _check_balance(reps, n_cells):
         # material residual: its scale is the energy the cycle moved through the material
         mat_scale = abs(r["pre_mat_E"]) + abs(r["absorbed_E"]) + abs(r["emission_E"])
         assert abs(r["mat_conservation"]) <= ref_tol * mat_scale, (r["step"], r["mat_conservation"], mat_scale)
+
+
+def _cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _photons_against_reference(deck, cycles, tmp_path):
+    """the device-mesh driver (validation mode: every photon's final record is written back) against the reference
+    harness stepping the same deck: reference src/replicated_driver.h:47-121, src/history_based_transport.h:279-308"""
+    from oracle import refio
+    if not refio.have_reference(deck.n_groups):
+        pytest.skip("oracle/_ref is not built (make -C oracle ref where /root/reference exists)")
+    deck = deck.with_(n_omp_threads=_cores(), dd_transport_type="REPLICATED")
+    dumps, out = refio.run_reference(deck, max_cycles=cycles, workdir=str(tmp_path), dump_level=1, timeout=1500)
+    ref = dumps[0]
+    d = driver.Driver(deck.write(str(tmp_path / f"{deck.name}_dev.xml")), n_groups=deck.n_groups, device=0,
+                      validate=True, mesh_on_device=True)
+    view = d.gpu_context()
+    for c in range(1, cycles + 1):
+        rep = d.cycle()
+        post = view.download(gpu.LIST_WORK)
+        n = int(ref[f"c{c}/n_photons"][0])
+        assert rep["gpu"]["n_transported"] == n, (c, rep["gpu"]["n_transported"], n)
+        assert n >= deck.photons
+        for k in ("cell", "group", "ctr", "descriptor"):
+            want = ref[f"c{c}/post/{k}"]
+            bad = np.flatnonzero(post[k] != want)
+            assert bad.size == 0, f"cycle {c}: {bad.size} of {n} photons differ in {k} (first: photon {bad[:5]})"
+        assert rep["gpu"]["n_census"] == int(ref[f"c{c}/n_census"][0])
+        for k in ("abs_E", "track_E", "T_e", "T_r"):
+            want = ref[f"c{c}/{k}"]
+            got = d.array(k)
+            assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want)), (c, k)
+        for k, rk in (("post_census_E", "post_census_E"), ("exit_E", "exit_E"), ("pre_census_E", "pre_census_E")):
+            want = float(ref[f"c{c}/{rk}"][0])
+            assert abs(rep[k] - want) <= 1e-9 * max(abs(want), 1e-300), (c, k, rep[k], want)
+    d.close()
+
+
+def test_hohlraum_single_node_photons_match_reference_at_full_size(tmp_path):
+    # configs[2] at its named size: 591 500 cells, 30 groups, 1e7 user photons per cycle (~1.05e7 transported)
+    _photons_against_reference(decks.hohlraum_single(t_stop=0.02), 2, tmp_path)
+
+
+def test_big_cube_photons_match_reference_at_2e7(tmp_path):
+    # configs[4] scaled to one GPU: 200^3 cells, 2e7 photons per cycle, all faces reflecting
+    _photons_against_reference(decks.big_cube(n=200, photons=20_000_000, t_stop=0.002), 2, tmp_path)
 
 
 def test_hohlraum_single_node_full_size(tmp_path):
