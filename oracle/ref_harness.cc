@@ -253,7 +253,13 @@ int main(int argc, char **argv) {
         d.f64(c + "E_source", mesh.get_source_E());
       }
       imc_state.set_pre_census_E(get_photon_list_E(census_photons));
+#ifdef BRANSON_B200_DROPIN
+      // the patched reference (oracle/dropin.patch): GPU_Setup holds the B200 device context, replicated_transport takes
+      // its gpu_transport_photons branch (bgpu_transport_photons_aos) when the deck says use_gpu_transporter TRUE
+      GPU_Setup gpu_setup(rank, n_ranks, imc_p.get_use_gpu_transporter_flag(), mesh.get_cells(), seed, n_user_photons);
+#else
       GPU_Setup gpu_setup(rank, n_ranks, false, mesh.get_cells());
+#endif
 
       auto t0 = std::chrono::high_resolution_clock::now();
       if (imc_state.get_step() == 1)

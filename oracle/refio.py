@@ -15,12 +15,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _DT = {0: np.float64, 1: np.uint32, 2: np.uint64, 3: np.uint8}
 
 
-def harness_path(n_groups: int) -> str:
-    return os.path.join(_HERE, "_ref", f"ref_harness_g{n_groups}")
+def harness_path(n_groups: int, dropin: bool = False) -> str:
+    """dropin: the reference with oracle/dropin.patch applied (its gpu_transport_photons calls the product library)"""
+    return os.path.join(_HERE, "_ref", f"ref_harness_{'dropin_' if dropin else ''}g{n_groups}")
 
 
-def stock_binary_path(n_groups: int) -> str:
-    return os.path.join(_HERE, "_ref", f"branson_ref_g{n_groups}")
+def stock_binary_path(n_groups: int, dropin: bool = False) -> str:
+    return os.path.join(_HERE, "_ref", f"branson_ref_{'dropin_' if dropin else ''}g{n_groups}")
 
 
 def have_reference(n_groups: int) -> bool:
@@ -49,12 +50,13 @@ def read_dump(path: str) -> dict:
 
 def run_reference(deck, n_ranks: int = 1, max_cycles: int | None = None, photon_limit: int | None = None,
                   workdir: str | None = None, timeout: float = 3600.0, comb_max: int | None = None,
-                  comb_stream: int = 0, dump_level: int = 0):
+                  comb_stream: int = 0, dump_level: int = 0, dropin: bool = False):
     """Returns (list of per-rank dump dicts, stdout of rank 0).  dump_level 1: per-photon integers of the
     post-transport list, abs_E / track_E / T_e / T_r and the scalars only (full-size runs)."""
-    exe = harness_path(deck.n_groups)
+    exe = harness_path(deck.n_groups, dropin)
     if not os.path.exists(exe):
-        raise FileNotFoundError(f"{exe} (build with `make -C oracle ref` where /root/reference exists)")
+        raise FileNotFoundError(f"{exe} (build with `make -C oracle ref{'_dropin' if dropin else ''}` where "
+                                "/root/reference exists)")
     tmp = workdir or tempfile.mkdtemp(prefix="branson_ref_")
     xml = deck.write(os.path.join(tmp, deck.name + ".xml"))
     prefix = os.path.join(tmp, deck.name)
