@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "event.cuh"
 #include "mesh_dev.cuh"
+#include "pool.cuh"
 #include "source.cuh"
 #include "transport.cuh"
 
@@ -104,6 +105,9 @@ struct bgpu_ctx {
   uint32_t tally_copies_live = 0;  // copies the zeroed scr_tally_rep currently holds (+1 for the main tally)
   uint64_t event_tail = 0;   // active-list size below which BGPU_EVENT hands over to the history kernel (0: auto)
   uint32_t event_passes = 0;
+  // BGPU_EVENT: 0 = event queues in shared memory (pool.cuh, default), 1 = lockstep passes through HBM (event.cuh)
+  int event_hbm = 0;
+  uint32_t pool_batch_scatter = 24, pool_batch_refill = 16;
 
   // device-resident mesh physics (bgpu_mesh_*, mesh_dev.cuh); allocated by bgpu_mesh_init
   bool mesh_ready = false;
@@ -476,6 +480,38 @@ int run_event(bgpu_ctx *c, TransportParams P) {
   return 0;
 }
 
+// BGPU_EVENT, default form: event queues in shared memory (pool.cuh); tallies and statistics as in the history launch
+int launch_pool(bgpu_ctx *c, const TransportParams &P) {
+  const size_t face_bytes = (size_t)P.mesh.n_faces * 8;
+  const bool use_smem = face_bytes <= 100 * 1024;
+  const size_t smem = 4 * POOL_BYTES_PER_WARP + (use_smem ? face_bytes : 0);
+  const bool ctrs = P.counters != nullptr;
+  const bool packed = P.uniform_groups != 0;
+  PoolParams Q{};
+  Q.T = P;
+  Q.batch_scatter = c->pool_batch_scatter;
+  Q.batch_refill = c->pool_batch_refill;
+  void (*kern)(const PoolParams) = nullptr;
+  if (packed) {
+    if (use_smem) kern = ctrs ? k_transport_pool<true, true, true> : k_transport_pool<false, true, true>;
+    else kern = ctrs ? k_transport_pool<true, false, true> : k_transport_pool<false, false, true>;
+  } else {
+    if (use_smem) kern = ctrs ? k_transport_pool<true, true, false> : k_transport_pool<false, true, false>;
+    else kern = ctrs ? k_transport_pool<true, false, false> : k_transport_pool<false, false, false>;
+  }
+  CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) return fail(c, "event-queue kernel: %zu bytes of shared memory per CTA do not fit", smem);
+  uint64_t blocks = (uint64_t)c->n_sm * per_sm;
+  const uint64_t max_useful = (P.n + 128 * POOL_ROWS - 1) / (128 * POOL_ROWS);
+  if (blocks > max_useful) blocks = std::max<uint64_t>(max_useful, 1);
+  ++c->launches;
+  kern<<<(unsigned)blocks, 128, smem, c->stream>>>(Q);
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
 // Replicated tallies (transport.cuh, TransportParams::tally_rep): as many copies as fit 64 MB (L2-sized), at most 64;
 // big meshes (8e6 cells) get none -- their deposits are spread over so many addresses that nothing serialises.  The
 // copies are zero between launches (k_fold_tally re-zeroes them).
@@ -557,7 +593,22 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   TransportParams P = make_params(c, writeback_all);
   if (algorithm == BGPU_EVENT) {
     if (tally_mode != BGPU_TALLY_ATOMIC) return fail(c, "the event-based variant supports BGPU_TALLY_ATOMIC only");
-    return run_event(c, P);
+    if (c->event_hbm) return run_event(c, P);
+    CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
+    if (prepare_tally_copies(c)) return 1;
+    const uint32_t copies = c->tally_copies_live;
+    if (copies > 1) {
+      P.tally_rep = (double2 *)c->scr_tally_rep.p;
+      P.tally_copies = copies;
+    }
+    if (launch_pool(c, P)) return 1;
+    if (copies > 1) {
+      ++c->launches;
+      k_fold_tally<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>((double2 *)c->d_tally, P.tally_rep,
+                                                                            c->mesh.n_cells, copies - 1);
+      CU(c, cudaGetLastError());
+    }
+    return 0;
   }
   if (tally_mode == BGPU_TALLY_ATOMIC) {
     CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
@@ -762,6 +813,9 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   if (const char *e = getenv("BGPU_SCATTER_BATCH")) { const int v = atoi(e); if (v >= 1 && v <= 32) { c->scatter_batch = (uint32_t)v; c->scatter_batch_auto = false; } }
   if (const char *e = getenv("BGPU_AGGREGATE")) c->aggregate = atoi(e) ? 1 : 0;
   if (const char *e = getenv("BGPU_TALLY_COPIES")) { const int v = atoi(e); if (v >= 0 && v <= 1024) c->tally_copies = v; }
+  if (const char *e = getenv("BGPU_EVENT_HBM")) c->event_hbm = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("BGPU_POOL_TS")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->pool_batch_scatter = (uint32_t)v; }
+  if (const char *e = getenv("BGPU_POOL_TR")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->pool_batch_refill = (uint32_t)v; }
   if (const char *e = getenv("BGPU_CHUNK")) { const int v = atoi(e); if (v > 0) { c->chunk = (uint32_t)v; c->chunk_auto = false; } }
   CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CUC(cudaEventCreate(&ev));
@@ -1932,6 +1986,15 @@ int bgpu_set_group_walk(bgpu_ctx *c, int closed_form) {
 int bgpu_set_event_tail(bgpu_ctx *c, uint64_t n_active) {
   if (!c) return 1;
   c->event_tail = n_active;
+  return 0;
+}
+
+int bgpu_set_event_mode(bgpu_ctx *c, int hbm_passes, int batch_scatter, int batch_refill) {
+  if (!c) return 1;
+  if (batch_scatter > 32 || batch_refill > 32) return fail(c, "bgpu_set_event_mode: batches are lane counts (1..32, 0 = keep)");
+  if (hbm_passes >= 0) c->event_hbm = hbm_passes ? 1 : 0;
+  if (batch_scatter > 0) c->pool_batch_scatter = (uint32_t)batch_scatter;
+  if (batch_refill > 0) c->pool_batch_refill = (uint32_t)batch_refill;
   return 0;
 }
 

@@ -227,6 +227,13 @@ int bgpu_set_tally_copies(bgpu_ctx *ctx, int copies);
 /* BGPU_EVENT: active-list size at or below which the lockstep passes hand the remaining histories to the persistent
  * history kernel (0 = auto: twice the number of resident lanes) */
 int bgpu_set_event_tail(bgpu_ctx *ctx, uint64_t n_active);
+/* BGPU_EVENT has two forms.  Default (hbm_passes = 0): event queues in shared memory (csrc/pool.cuh) -- every lane owns
+ * two photon slots, each trip the warp elects the event type most lanes can serve (advance / scatter / retire+refill)
+ * and runs that block alone: the regrouping of the reference's event_based_transport.h at warp scope, without HBM
+ * traffic.  batch_scatter / batch_refill = lanes that must hold a parked scatter / a finished or empty slot before that
+ * block is elected over a fuller advance block (0 = keep; defaults 24 / 16).  hbm_passes = 1: the first form, lockstep
+ * passes over active lists in HBM (csrc/event.cuh; bgpu_set_event_tail applies to it); < 0 keeps the current form. */
+int bgpu_set_event_mode(bgpu_ctx *ctx, int hbm_passes, int batch_scatter, int batch_refill);
 /* sample_emission_group (src/sampling_functions.h:126-138): 1 (default) = when every cell's groups are equal, use the
  * provably-equivalent closed form of the sequential walk; 0 = always walk the group array like the reference */
 int bgpu_set_group_walk(bgpu_ctx *ctx, int closed_form);
