@@ -503,6 +503,7 @@ int launch_pool(bgpu_ctx *c, const TransportParams &P) {
   int per_sm = 0;
   CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
   if (per_sm < 1) return fail(c, "event-queue kernel: %zu bytes of shared memory per CTA do not fit", smem);
+  if (c->blocks_per_sm > 0 && c->blocks_per_sm < per_sm) per_sm = c->blocks_per_sm;
   uint64_t blocks = (uint64_t)c->n_sm * per_sm;
   const uint64_t max_useful = (P.n + 128 * POOL_ROWS - 1) / (128 * POOL_ROWS);
   if (blocks > max_useful) blocks = std::max<uint64_t>(max_useful, 1);

@@ -66,7 +66,7 @@ EXPORTS = [
     "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
     "bgpu_mesh_update_temperature", "bgpu_mesh_get", "bgpu_mesh_calculate_photon_energy_replicated",
     "bgpu_mesh_finish_cycle", "bgpu_comm_unique_id", "bgpu_comm_init_rank", "bgpu_comm_init_local", "bgpu_comm_info",
-    "bgpu_comm_allreduce_host", "bgpu_comm_allreduce_tallies",
+    "bgpu_comm_allreduce_host", "bgpu_comm_allreduce_tallies", "bgpu_set_event_mode",
 ]
 COMM_NONE, COMM_NCCL, COMM_LOCAL = 0, 1, 2
 
@@ -108,6 +108,7 @@ def lib():
         L.bgpu_sort_census_by_cell.argtypes = [vp]
         L.bgpu_set_tally_copies.argtypes = [vp, i32]
         L.bgpu_set_event_tail.argtypes = [vp, u64]
+        L.bgpu_set_event_mode.argtypes = [vp, i32, i32, i32]
         L.bgpu_set_group_walk.argtypes = [vp, i32]
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
         L.bgpu_test_threefry.argtypes = [vp, vp]
@@ -262,6 +263,10 @@ class Context:
 
     def set_event_tail(self, n_active):
         self._ck(lib().bgpu_set_event_tail(self._h, n_active))
+
+    def set_event_mode(self, hbm_passes=-1, batch_scatter=0, batch_refill=0):
+        """BGPU_EVENT: shared-memory event queues (default) or the HBM-pass form; queue election thresholds"""
+        self._ck(lib().bgpu_set_event_mode(self._h, hbm_passes, batch_scatter, batch_refill))
 
     def set_group_walk(self, closed_form=True):
         self._ck(lib().bgpu_set_group_walk(self._h, 1 if closed_form else 0))

@@ -36,7 +36,7 @@ _LOOKUPS = {}
 
 
 def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATOMIC, max_cycles=None, launch=None,
-                event_tail=None, closed_form_walk=True, group_arrays=False, tuning=None):
+                event_tail=None, closed_form_walk=True, group_arrays=False, tuning=None, event_queue=None):
     sim = port.OracleSim(deck, n_ranks=n_ranks)
     ctxs = None
     cyc = 0
@@ -51,8 +51,11 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
                 c.enable_counters(True)
                 if launch:
                     c.set_launch(**launch)
-                if event_tail is not None:
+                if event_tail is not None:  # the HBM-pass form of the event variant (csrc/event.cuh)
+                    c.set_event_mode(hbm_passes=1)
                     c.set_event_tail(event_tail)
+                if event_queue is not None:  # the shared-memory queue form (csrc/pool.cuh): election thresholds
+                    c.set_event_mode(hbm_passes=0, batch_scatter=event_queue[0], batch_refill=event_queue[1])
                 c.set_group_walk(closed_form_walk)
                 if tuning:
                     c.set_divergence(tuning.get("scatter_batch", 0), tuning.get("aggregate", -1))
@@ -186,6 +189,23 @@ def test_full_mesh_hohlraum_matches_oracle_photon_by_photon():
 def test_history_deterministic_matches_oracle(name):
     mk, n_ranks = CASES[name]
     _run_cycles(mk(), n_ranks=n_ranks, tally_mode=gpu.TALLY_DETERMINISTIC)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("event_queue", [(24, 16), (1, 1), (32, 32), (7, 29)])
+def test_event_queue_variant_matches_oracle(name, event_queue):
+    """BGPU_EVENT, default form (csrc/pool.cuh: event queues in shared memory, two photon slots per lane, one event type
+    per warp trip): the regrouping must not change a bit of any photon -- every per-photon integer against the oracle,
+    for the default election thresholds, for 'serve every event at once' (1, 1), for 'wait for a full warp' (32, 32) and
+    for an odd pair."""
+    mk, n_ranks = CASES[name]
+    _run_cycles(mk(), n_ranks=n_ranks, algorithm=gpu.EVENT, event_queue=event_queue, max_cycles=3)
+
+
+def test_event_queue_variant_small_chunks_and_tally_copies():
+    _run_cycles(decks.hot_zone(photons=20000, t_stop=0.02, scale=10), algorithm=gpu.EVENT,
+                launch=dict(blocks_per_sm=1, chunk=7), tuning=dict(tally_copies=7))
+    _run_cycles(decks.marshak_wave(photons=20000, t_stop=0.03), algorithm=gpu.EVENT, tuning=dict(tally_copies=64))
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
