@@ -108,6 +108,12 @@ struct bgpu_ctx {
   // BGPU_EVENT: 0 = event queues in shared memory (pool.cuh, default), 1 = lockstep passes through HBM (event.cuh)
   int event_hbm = 0;
   uint32_t pool_batch_scatter = 24, pool_batch_refill = 16;
+  // BGPU_HISTORY: which kernel runs the histories (per-photon results are identical): 0 = auto -- the event-queue kernel
+  // on decks that MIX event types (previous launch: >= 16 events per history, 8..45 % of them scatters: big_cube,
+  // hot_zone), the history kernel elsewhere; 1 = always the history kernel; 2 = always the event queues
+  int kernel_choice = 0;
+  double prev_scatter_fraction = 0.0;
+  uint32_t kernel_used = 0;  // of the last transport: 0 history, 1 event queues, 2 event passes through HBM
 
   // device-resident mesh physics (bgpu_mesh_*, mesh_dev.cuh); allocated by bgpu_mesh_init
   bool mesh_ready = false;
@@ -592,8 +598,10 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   if (c->n_work >= (1ull << 32)) return fail(c, "bgpu_transport: %llu photons in one work list (limit 2^32 - 1)",
                                              (unsigned long long)c->n_work);
   TransportParams P = make_params(c, writeback_all);
+  c->kernel_used = 0u;
   if (algorithm == BGPU_EVENT) {
     if (tally_mode != BGPU_TALLY_ATOMIC) return fail(c, "the event-based variant supports BGPU_TALLY_ATOMIC only");
+    c->kernel_used = c->event_hbm ? 2u : 1u;
     if (c->event_hbm) return run_event(c, P);
     CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
     if (prepare_tally_copies(c)) return 1;
@@ -619,7 +627,14 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
       P.tally_rep = (double2 *)c->scr_tally_rep.p;
       P.tally_copies = copies;
     }
-    if (launch_history<TM_ATOMIC>(c, P)) return 1;
+    // Mixed decks lose a third of their lanes to divergence in the history kernel; the event-queue kernel regroups them
+    // (pool.cuh; big_cube 22 -> 28 lanes per instruction, +6 % histories/s; profiles/pool_variants_r02.txt).  It loses on
+    // scattering-dominated decks (every lane scatters on every trip anyway) and on short histories.
+    const bool mixed = c->prev_events_per_history >= 16.0 && c->prev_scatter_fraction >= 0.08 &&
+                       c->prev_scatter_fraction <= 0.45;
+    const bool queues = c->kernel_choice == 2 || (c->kernel_choice == 0 && mixed);
+    c->kernel_used = queues ? 1u : 0u;
+    if (queues ? launch_pool(c, P) : launch_history<TM_ATOMIC>(c, P)) return 1;
     if (copies > 1) {
       ++c->launches;
       k_fold_tally<<<grid_for(c->mesh.n_cells, 256), 256, 0, c->stream>>>((double2 *)c->d_tally, P.tally_rep,
@@ -745,6 +760,8 @@ int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
   s.n_group_lookups = st[ST_LOOKUPS];
   s.n_launches = c->launches;
   if (s.n_transported) c->prev_events_per_history = (double)s.n_events / (double)s.n_transported;
+  if (s.n_events) c->prev_scatter_fraction = (double)s.n_scatters / (double)s.n_events;
+  s.transport_kernel = c->kernel_used;
   return 0;
 }
 
@@ -815,6 +832,10 @@ int bgpu_create(bgpu_ctx **out, const bgpu_mesh_desc *d) {
   if (const char *e = getenv("BGPU_AGGREGATE")) c->aggregate = atoi(e) ? 1 : 0;
   if (const char *e = getenv("BGPU_TALLY_COPIES")) { const int v = atoi(e); if (v >= 0 && v <= 1024) c->tally_copies = v; }
   if (const char *e = getenv("BGPU_EVENT_HBM")) c->event_hbm = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("BGPU_KERNEL")) {
+    const std::string k(e);
+    c->kernel_choice = k == "history" ? 1 : (k == "queues" ? 2 : 0);
+  }
   if (const char *e = getenv("BGPU_POOL_TS")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->pool_batch_scatter = (uint32_t)v; }
   if (const char *e = getenv("BGPU_POOL_TR")) { const int v = atoi(e); if (v >= 1 && v <= 32) c->pool_batch_refill = (uint32_t)v; }
   if (const char *e = getenv("BGPU_CHUNK")) { const int v = atoi(e); if (v > 0) { c->chunk = (uint32_t)v; c->chunk_auto = false; } }
@@ -1987,6 +2008,13 @@ int bgpu_set_group_walk(bgpu_ctx *c, int closed_form) {
 int bgpu_set_event_tail(bgpu_ctx *c, uint64_t n_active) {
   if (!c) return 1;
   c->event_tail = n_active;
+  return 0;
+}
+
+int bgpu_set_kernel(bgpu_ctx *c, int choice) {
+  if (!c) return 1;
+  if (choice < 0 || choice > 2) return fail(c, "bgpu_set_kernel: 0 (auto), 1 (history kernel), 2 (event queues)");
+  c->kernel_choice = choice;
   return 0;
 }
 

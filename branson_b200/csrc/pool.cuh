@@ -8,15 +8,18 @@
 // pass streams the photon state out and back, which costs 8-10x on scattering decks.  Here the regrouping costs shared
 // memory traffic only:
 //
-//   * every lane owns POOL_ROWS photon slots in shared memory (176 bytes each, eleven 16-byte vectors laid out
-//     [vector][lane] so that a warp's access to one vector of one row is a conflict-free 512-byte LDS.128 / STS.128);
+//   * every warp keeps 8 * POOL_K = 56 photon slots in shared memory (176 bytes each, eleven 16-byte vectors laid out
+//     [vector][slot], so vector v of slot s sits in the 16-byte bank group s % 8); the slots are shared by "classes" of
+//     four lanes -- lanes l, l + 8, l + 16, l + 24 own the slots s with s % 8 == l % 8 -- so the eight lanes of a quarter warp
+//     always touch eight different bank groups: every LDS.128 / STS.128 is conflict-free whichever slots are picked;
 //   * a slot is EMPTY, ADVANCE (next: one trip of the reference's loop), SCATTER (parked at a scatter) or DONE (history
-//     finished, record not written yet);
-//   * each trip the warp votes on ONE event type -- the one most lanes can serve from either of their slots -- and runs
-//     that block for those lanes: A (advance_event: distance sampling, implicit capture, boundary handling), S
-//     (scatter_event: the angle draws and the group), R (write the finished record, fetch the next photon of the work
-//     list into the slot).  With two slots per lane a lane almost always holds a photon of the elected type, so each
-//     block runs at ~30 lanes instead of 27 / 14 / 7.
+//     finished, record not written yet); a class's eight slot states live in one register (four 8-bit masks) that its
+//     four lanes keep in step with two shuffles per trip;
+//   * each trip the warp votes on ONE event type -- the one most lanes can serve -- and runs that block alone: A
+//     (advance_event: distance sampling, implicit capture, boundary handling), S (scatter_event: the angle draws and
+//     the group), R (write the finished record, fetch the next photon of the work list into the slot); the k-th lane of
+//     a class takes the class's k-th slot of the elected type.  With seven slots behind four lanes a lane almost
+//     always finds one, so every block runs near full width instead of 27 / 14 / 7 lanes.
 //
 // The blocks are the SAME device functions the history kernel runs (transport.cuh), per photon in the same order, so the
 // per-photon results are identical by construction (reference SURVEY note N5: a history depends on nothing but its own
@@ -26,14 +29,18 @@
 
 namespace bg {
 
-#ifndef POOL_ROWS
-#define POOL_ROWS 2
+// slots per class of four lanes (<= 8: one byte of the mask register per state).  Seven slots (1.75 per lane) leave
+// room for five CTAs per SM instead of four; A/B in profiles/pool_variants_r02.txt
+#ifndef POOL_K
+#define POOL_K 7
 #endif
 #ifndef POOL_MIN_BLOCKS
-#define POOL_MIN_BLOCKS 4
+#define POOL_MIN_BLOCKS 5
 #endif
+#define POOL_ROWS 2  // (work-list photons per resident thread the launcher assumes when it trims the grid)
 
-enum : uint32_t { PM_EMPTY = 0u, PM_ADV = 1u, PM_SCAT = 2u, PM_DONE = 3u };
+// slot states = byte index of the class's mask register
+enum : uint32_t { PM_ADV = 0u, PM_SCAT = 1u, PM_DONE = 2u, PM_EMPTY = 3u };
 // vectors of a slot (16 bytes each)
 enum : int {
   PV_XY = 0,    // x, y
@@ -49,17 +56,19 @@ enum : int {
   PV_SCT,       // c_sc, grp_cell, grp_ctr32, idx  (written by the S block)
   PV_N
 };
-constexpr size_t POOL_BYTES_PER_WARP = (size_t)POOL_ROWS * PV_N * 32 * 16;
+constexpr int POOL_SLOTS = 8 * POOL_K;  // per warp (slot s = 8 j + class, j < POOL_K)
+constexpr size_t POOL_BYTES_PER_WARP = (size_t)POOL_SLOTS * PV_N * 16;
+constexpr int PV_STRIDE = POOL_SLOTS * 16;  // bytes between consecutive vectors of a slot
 
 struct PoolSlot {
-  char *base;  // this lane's column of one row: vector v at base + v * 512
-  __device__ __forceinline__ double2 ld2(int v) const { return *reinterpret_cast<const double2 *>(base + v * 512); }
-  __device__ __forceinline__ uint4 ld4(int v) const { return *reinterpret_cast<const uint4 *>(base + v * 512); }
+  char *base;  // vector v of this slot at base + v * PV_STRIDE
+  __device__ __forceinline__ double2 ld2(int v) const { return *reinterpret_cast<const double2 *>(base + v * PV_STRIDE); }
+  __device__ __forceinline__ uint4 ld4(int v) const { return *reinterpret_cast<const uint4 *>(base + v * PV_STRIDE); }
   __device__ __forceinline__ void st2(int v, double a, double b) const {
-    *reinterpret_cast<double2 *>(base + v * 512) = make_double2(a, b);
+    *reinterpret_cast<double2 *>(base + v * PV_STRIDE) = make_double2(a, b);
   }
   __device__ __forceinline__ void st4(int v, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
-    *reinterpret_cast<uint4 *>(base + v * 512) = make_uint4(a, b, c, d);
+    *reinterpret_cast<uint4 *>(base + v * PV_STRIDE) = make_uint4(a, b, c, d);
   }
 };
 
@@ -133,8 +142,17 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
   const unsigned lt_mask = (1u << lane_id) - 1u;
   const uint32_t n_total = (uint32_t)P.n;
   const uint32_t bcpack = pack_bc(P.mesh.bc);
-  char *const my_pool = s_dyn + warp_id * POOL_BYTES_PER_WARP + lane_id * 16;
-  auto slot_of = [&](uint32_t row) { return PoolSlot{my_pool + (size_t)row * (PV_N * 512)}; };
+  // this lane's class (l % 8) and its rank inside the class (l / 8): the rank-th slot of the elected state is its slot
+  const uint32_t cls = lane_id & 7u, rank = lane_id >> 3;
+  char *const cls_pool = s_dyn + warp_id * POOL_BYTES_PER_WARP + cls * 16;
+  auto slot_of = [&](int j) { return PoolSlot{cls_pool + (size_t)j * 128}; };  // slot s = 8 j + cls: byte offset 16 s
+  // the j of the class's rank-th slot whose bit is set in the 8-bit mask m, or -1
+  auto pick = [&](uint32_t m) {
+    m &= 0xffu;
+#pragma unroll
+    for (uint32_t i = 0; i < 3; ++i) m = (i < rank) ? (m & (m - 1u)) : m;
+    return m ? (int)__ffs((int)m) - 1 : -1;
+  };
 
   double2 *my_tally = P.tally;
   if (P.tally_copies > 1u) {
@@ -148,24 +166,18 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
     }
   };
 
-  uint32_t mode[POOL_ROWS];
-#pragma unroll
-  for (int r = 0; r < POOL_ROWS; ++r) mode[r] = PM_EMPTY;
+  // the class's slot states: byte PM_x = mask of the slots in state x (identical in the four lanes of the class)
+  uint32_t masks = ((1u << POOL_K) - 1u) << (8 * PM_EMPTY);
   uint32_t q_next = 0, q_end = 0;  // the warp's chunk of the work list (warp-uniform)
   bool exhausted = false;
   LaneStats LS{0u, 0u, 0u, 0u, 0u};
   const uint32_t T_S = Q.batch_scatter, T_R = Q.batch_refill;
 
   for (;;) {
-    bool hasA = false, hasS = false, hasD = false, hasE = false;
-#pragma unroll
-    for (int r = 0; r < POOL_ROWS; ++r) {
-      hasA = hasA || mode[r] == PM_ADV;
-      hasS = hasS || mode[r] == PM_SCAT;
-      hasD = hasD || mode[r] == PM_DONE;
-      hasE = hasE || mode[r] == PM_EMPTY;
-    }
-    const bool hasR = hasD || (hasE && !exhausted);
+    const uint32_t mA = masks >> (8 * PM_ADV), mS = masks >> (8 * PM_SCAT);
+    const uint32_t mR = (masks >> (8 * PM_DONE)) | (exhausted ? 0u : (masks >> (8 * PM_EMPTY)));
+    const bool hasA = rank < (uint32_t)__popc(mA & 0xffu), hasS = rank < (uint32_t)__popc(mS & 0xffu);
+    const bool hasR = rank < (uint32_t)__popc(mR & 0xffu);
     const unsigned bA = __ballot_sync(FULL, hasA), bS = __ballot_sync(FULL, hasS), bR = __ballot_sync(FULL, hasR);
     if ((bA | bS | bR) == 0u) break;
     const uint32_t nA = __popc(bA), nS = __popc(bS), nR = __popc(bR);
@@ -174,14 +186,13 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
     if (nR && (nR >= T_R || (nR >= nA && nR >= nS))) block = 2;
     else if (nS && (nS >= T_S || nS >= nA)) block = 1;
     else block = 0;
+    uint32_t moved = 0u;  // this lane's slot in its new state's byte (the class ORs these together below)
 
     if (block == 0) {
       // ---------------- A: one trip of the reference's loop up to the event dispatch ----------------
       if (hasA) {
-        uint32_t row = 0;
-#pragma unroll
-        for (int r = POOL_ROWS - 1; r >= 0; --r) row = (mode[r] == PM_ADV) ? (uint32_t)r : row;
-        const PoolSlot sl = slot_of(row);
+        const int j = pick(mA);
+        const PoolSlot sl = slot_of(j);
         PState S;
         uint32_t idx;
         uint8_t descriptor;
@@ -195,8 +206,7 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
           close_visit(S, C, 1u);
           m = PM_DONE;
         }
-#pragma unroll
-        for (int r = 0; r < POOL_ROWS; ++r) mode[r] = ((uint32_t)r == row) ? m : mode[r];
+        moved = (1u << j) << (8 * m);
         sl.st2(PV_XY, S.x, S.y);
         sl.st2(PV_ZL, S.z, S.life);
         sl.st2(PV_AZC, S.az, __longlong_as_double((long long)S.ctr));
@@ -211,10 +221,8 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
     } else if (block == 1) {
       // ---------------- S: the parked scatters, sampled together ----------------
       if (hasS) {
-        uint32_t row = 0;
-#pragma unroll
-        for (int r = POOL_ROWS - 1; r >= 0; --r) row = (mode[r] == PM_SCAT) ? (uint32_t)r : row;
-        const PoolSlot sl = slot_of(row);
+        const int j = pick(mS);
+        const PoolSlot sl = slot_of(j);
         PState S;
         const double2 azc = sl.ld2(PV_AZC), sg = sl.ld2(PV_SG), fa = sl.ld2(PV_FA);
         const uint4 sk = sl.ld4(PV_SK), sct = sl.ld4(PV_SCT);
@@ -227,8 +235,7 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
         S.p_grp = 0.0;
         const uint32_t group0 = S.group;
         scatter_event<true>(S, C, bS);
-#pragma unroll
-        for (int r = 0; r < POOL_ROWS; ++r) mode[r] = ((uint32_t)r == row) ? PM_ADV : mode[r];
+        moved = (1u << j) << (8 * PM_ADV);
         sl.st2(PV_AXY, S.ax, S.ay);
         sl.st2(PV_AZC, S.az, __longlong_as_double((long long)S.ctr));
         sl.st4(PV_SCT, S.c_sc, S.grp_cell, S.grp_ctr32, sct.w);
@@ -241,18 +248,24 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
       }
     } else {
       // ---------------- R: write finished records, fetch the next photons ----------------
-      // one slot per lane and trip: a finished one first, else an empty one
-      uint32_t row = 0;
-      bool retire = false, fill = false;
+      // the class's finished slots first, then its empty ones
+      int j = -1;
+      bool retire = false;
       if (hasR) {
+        const uint32_t mD = (masks >> (8 * PM_DONE)) & 0xffu;
+        // rank-th slot of (finished, then empty): the finished ones occupy the first ranks
+        const uint32_t nD = (uint32_t)__popc(mD);
+        if (rank < nD) {
+          j = pick(mD);
+          retire = true;
+        } else {
+          uint32_t m = (masks >> (8 * PM_EMPTY)) & 0xffu;
 #pragma unroll
-        for (int r = POOL_ROWS - 1; r >= 0; --r) row = (mode[r] == PM_EMPTY) ? (uint32_t)r : row;
-#pragma unroll
-        for (int r = POOL_ROWS - 1; r >= 0; --r) row = (mode[r] == PM_DONE) ? (uint32_t)r : row;
-        retire = hasD;
-        fill = !exhausted;
+          for (uint32_t i = 0; i < 3; ++i) m = (i + nD < rank) ? (m & (m - 1u)) : m;
+          j = m ? (int)__ffs((int)m) - 1 : -1;
+        }
       }
-      const PoolSlot sl = slot_of(row);
+      const PoolSlot sl = slot_of(j < 0 ? 0 : j);
       if (retire) {
         PState S;
         uint32_t idx;
@@ -267,10 +280,10 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
         if (full) pstate_store_full(S, P.ph, idx);
         if (COUNTERS)
           reinterpret_cast<uint4 *>(P.counters)[idx] = make_uint4(events_of_finished(S), S.c_sc, S.c_cr, S.c_rf);
-#pragma unroll
-        for (int r = 0; r < POOL_ROWS; ++r) mode[r] = ((uint32_t)r == row) ? PM_EMPTY : mode[r];
+        moved = (1u << j) << (8 * PM_EMPTY);
       }
       // refill (warp-uniform chunk bookkeeping, as in k_transport_history)
+      const bool fill = j >= 0 && !exhausted;
       const unsigned want = __ballot_sync(FULL, fill);
       if (want) {
         if (q_next == q_end) {
@@ -301,15 +314,19 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
             sl.st2(PV_LOC, 0.0, 0.0);
             sl.st4(PV_CNT, 0u, 0u, 0u, 0u);
             sl.st4(PV_SCT, 0u, ~0u, 0u, idx);
-#pragma unroll
-            for (int r = 0; r < POOL_ROWS; ++r) mode[r] = ((uint32_t)r == row) ? PM_ADV : mode[r];
+            moved = (1u << j) << (8 * PM_ADV);
           }
           const uint32_t asked = __popc(want);
           q_next += (asked < avail) ? asked : avail;
         }
       }
     }
-    __syncwarp();
+    // the class's four lanes merge what they moved: a moved slot leaves whatever state it was in
+    moved |= __shfl_xor_sync(FULL, moved, 8);
+    moved |= __shfl_xor_sync(FULL, moved, 16);
+    uint32_t touched = moved | (moved >> 16);
+    touched = (touched | (touched >> 8)) & 0xffu;
+    masks = (masks & ~(touched * 0x01010101u)) | moved;
   }
 
   lane_stats_flush(s_stats, LS);

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.environ.get("BRANSON_LIB_DIR") or _HERE
 LIB_PATH = os.path.join(LIB_DIR, "libbranson_gpu.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 HISTORY, EVENT = 0, 1
 TALLY_ATOMIC, TALLY_DETERMINISTIC = 0, 1
 LIST_WORK, LIST_CENSUS = 0, 1
@@ -39,7 +39,8 @@ class CycleStats(C.Structure):
                 ("n_scatters", C.c_uint64), ("n_crossings", C.c_uint64), ("n_reflections", C.c_uint64),
                 ("n_deposits", C.c_uint64), ("n_group_lookups", C.c_uint64), ("n_launches", C.c_uint64),
                 ("ms_source", C.c_float),
-                ("ms_transport", C.c_float), ("ms_census", C.c_float), ("ms_total", C.c_float)]
+                ("ms_transport", C.c_float), ("ms_census", C.c_float), ("ms_total", C.c_float),
+                ("transport_kernel", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -66,8 +67,9 @@ EXPORTS = [
     "bgpu_mesh_init", "bgpu_mesh_calculate_photon_energy", "bgpu_mesh_redistribute", "bgpu_mesh_source",
     "bgpu_mesh_update_temperature", "bgpu_mesh_get", "bgpu_mesh_calculate_photon_energy_replicated",
     "bgpu_mesh_finish_cycle", "bgpu_comm_unique_id", "bgpu_comm_init_rank", "bgpu_comm_init_local", "bgpu_comm_info",
-    "bgpu_comm_allreduce_host", "bgpu_comm_allreduce_tallies", "bgpu_set_event_mode",
+    "bgpu_comm_allreduce_host", "bgpu_comm_allreduce_tallies", "bgpu_set_event_mode", "bgpu_set_kernel",
 ]
+KERNEL_AUTO, KERNEL_HISTORY, KERNEL_QUEUES = 0, 1, 2
 COMM_NONE, COMM_NCCL, COMM_LOCAL = 0, 1, 2
 
 
@@ -109,6 +111,7 @@ def lib():
         L.bgpu_set_tally_copies.argtypes = [vp, i32]
         L.bgpu_set_event_tail.argtypes = [vp, u64]
         L.bgpu_set_event_mode.argtypes = [vp, i32, i32, i32]
+        L.bgpu_set_kernel.argtypes = [vp, i32]
         L.bgpu_set_group_walk.argtypes = [vp, i32]
         L.bgpu_test_rng_draws.argtypes = [u32, u64, u32, vp]
         L.bgpu_test_threefry.argtypes = [vp, vp]
@@ -263,6 +266,10 @@ class Context:
 
     def set_event_tail(self, n_active):
         self._ck(lib().bgpu_set_event_tail(self._h, n_active))
+
+    def set_kernel(self, choice=KERNEL_AUTO):
+        """BGPU_HISTORY: auto / always the history kernel / always the event-queue kernel"""
+        self._ck(lib().bgpu_set_kernel(self._h, choice))
 
     def set_event_mode(self, hbm_passes=-1, batch_scatter=0, batch_refill=0):
         """BGPU_EVENT: shared-memory event queues (default) or the HBM-pass form; queue election thresholds"""

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BGPU_ABI_VERSION 1
+#define BGPU_ABI_VERSION 2
 
 /* Constants::bc_type, reference src/constants.h:28 */
 enum { BGPU_REFLECT = 0, BGPU_VACUUM = 1, BGPU_ELEMENT = 2, BGPU_SOURCE = 3, BGPU_PROCESSOR = 4 };
@@ -85,6 +85,8 @@ typedef struct {
   uint64_t n_launches; /* kernels launched through this ctx since bgpu_create (cumulative) */
   /* device times (CUDA events on the ctx stream), milliseconds */
   float ms_source, ms_transport, ms_census, ms_total;
+  uint32_t transport_kernel; /* which kernel ran the histories: 0 history, 1 event queues (shared memory), 2 event passes */
+  uint32_t reserved;
 } bgpu_cycle_stats;
 
 /* host-side SoA view used by bgpu_upload_photons / bgpu_download_photons (validation and tests).  Any pointer may be
@@ -227,6 +229,11 @@ int bgpu_set_tally_copies(bgpu_ctx *ctx, int copies);
 /* BGPU_EVENT: active-list size at or below which the lockstep passes hand the remaining histories to the persistent
  * history kernel (0 = auto: twice the number of resident lanes) */
 int bgpu_set_event_tail(bgpu_ctx *ctx, uint64_t n_active);
+/* BGPU_HISTORY: which kernel runs the histories.  0 (default) = auto: the event-queue kernel (see below) on decks that mix
+ * event types -- the previous launch saw >= 16 events per history with 8..45 % of them scatters (big_cube, hot_zone), where
+ * the history kernel loses a third of its lanes to divergence -- and the history kernel elsewhere; 1 = always the history
+ * kernel; 2 = always the event queues.  Per-photon results do not depend on the choice (tests/test_gpu_parity.py). */
+int bgpu_set_kernel(bgpu_ctx *ctx, int choice);
 /* BGPU_EVENT has two forms.  Default (hbm_passes = 0): event queues in shared memory (csrc/pool.cuh) -- every lane owns
  * two photon slots, each trip the warp elects the event type most lanes can serve (advance / scatter / retire+refill)
  * and runs that block alone: the regrouping of the reference's event_based_transport.h at warp scope, without HBM

@@ -60,6 +60,8 @@ def _run_cycles(deck, n_ranks=1, algorithm=gpu.HISTORY, tally_mode=gpu.TALLY_ATO
                 if tuning:
                     c.set_divergence(tuning.get("scatter_batch", 0), tuning.get("aggregate", -1))
                     c.set_tally_copies(tuning.get("tally_copies", 0))
+                    if "kernel" in tuning:
+                        c.set_kernel(tuning["kernel"])
         dt, next_dt, gse = sim.get("dt")[0], sim.get("next_dt")[0], sim.get("global_source_energy")[0]
         f, op_a, op_s = sim.get("f"), sim.get("op_a"), sim.get("op_s")
         tot_abs = np.zeros(deck.n_cells)
@@ -258,6 +260,8 @@ def test_small_chunks_and_few_blocks_give_identical_photons():
     dict(scatter_batch=32, aggregate=1, tally_copies=1),   # scatters wait for a full warp; warp-aggregated deposits
     dict(scatter_batch=5, aggregate=1, tally_copies=7),    # odd sizes; replicated tallies folded after the launch
     dict(scatter_batch=12, aggregate=0, tally_copies=64),
+    dict(kernel=gpu.KERNEL_QUEUES, tally_copies=7),        # BGPU_HISTORY served by the event-queue kernel (csrc/pool.cuh)
+    dict(kernel=gpu.KERNEL_HISTORY),                       # ... and pinned to the history kernel (no auto switch)
 ])
 def test_divergence_and_contention_knobs_do_not_change_results(name, tuning):
     """Parking scatters, combining same-cell deposits inside a warp and replicating the tally array only regroup work

@@ -142,6 +142,7 @@ def run_case(name, deck, cycles, algorithm, sort_census=False):
             "hbm_frac": ab / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
             "Gdraws_per_s": (g["n_events"] + 4 * g["n_scatters"]) / (ms * 1e-3) / 1e9 if ms > 0 else None,
             "rad_balance_rel": abs(r["rad_balance_exact"]) / max(1e-300, r["pre_census_E"] + r["emission_E"] + r["source_E"]),
+            "kernel": {0: "history", 1: "queues", 2: "passes"}.get(g.get("transport_kernel", 0), "?"),
         })
     d.close()
     return {"deck": name, "n_groups": deck.n_groups, "photons": deck.photons,
@@ -167,12 +168,12 @@ def main():
         res = run_case(name, deck, cycles, algo, a.sort_census)
         out.append(res)
         print(f"== {name}  (G={deck.n_groups}, photons={deck.photons:.3g})")
-        print("  cyc   transported     ms    Mhist/s  ev/h  sc/h  cr/h   B/hist   GB/s  hbm%  Gdraw/s")
+        print("  cyc   transported     ms    Mhist/s  ev/h  sc/h  cr/h   B/hist   GB/s  hbm%  Gdraw/s  kernel")
         for r in res["cycles"]:
             print(f"  {r['cycle']:3d} {r['n_transported']:13d} {r['ms_transport']:7.2f} {r['histories_per_s'] / 1e6:9.1f}"
                   f" {r['events_per_history']:5.1f} {r['scatters_per_history']:5.1f} {r['crossings_per_history']:5.1f}"
                   f" {r['bytes_per_history']:8.0f} {r['achieved_GBs']:6.0f} {100 * r['hbm_frac']:5.1f}"
-                  f" {r['Gdraws_per_s']:7.1f}", flush=True)
+                  f" {r['Gdraws_per_s']:7.1f}  {r['kernel']}", flush=True)
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(out, fh, indent=1)

@@ -28,6 +28,11 @@ KEYS = [
     "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_op_read_hit_rate.pct", "lts__t_sector_op_red_hit_rate.pct",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "lts__average_t_sector_hit_rate_realtime.pct",
+    "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.per_cycle_active", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+    "smsp__inst_executed.avg.per_cycle_active",
 ]
 lines = [f"# ncu --set full summary of `{rep}`", ""]
 traffic = []
