@@ -630,8 +630,10 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
     // Mixed decks lose a third of their lanes to divergence in the history kernel; the event-queue kernel regroups them
     // (pool.cuh; big_cube 22 -> 28 lanes per instruction, +6 % histories/s; profiles/pool_variants_r02.txt).  It loses on
     // scattering-dominated decks (every lane scatters on every trip anyway) and on short histories.
+    // (hot_zone at 1e6 photons: 767 against 718 M histories/s; at 1e7: 882 against 837; a list that does not even fill
+    // the resident slots a few times is left to the history kernel)
     const bool mixed = c->prev_events_per_history >= 16.0 && c->prev_scatter_fraction >= 0.08 &&
-                       c->prev_scatter_fraction <= 0.45;
+                       c->prev_scatter_fraction <= 0.45 && c->n_work >= 500000ull;
     const bool queues = c->kernel_choice == 2 || (c->kernel_choice == 0 && mixed);
     c->kernel_used = queues ? 1u : 0u;
     if (queues ? launch_pool(c, P) : launch_history<TM_ATOMIC>(c, P)) return 1;

@@ -230,7 +230,7 @@ int bgpu_set_tally_copies(bgpu_ctx *ctx, int copies);
  * history kernel (0 = auto: twice the number of resident lanes) */
 int bgpu_set_event_tail(bgpu_ctx *ctx, uint64_t n_active);
 /* BGPU_HISTORY: which kernel runs the histories.  0 (default) = auto: the event-queue kernel (see below) on decks that mix
- * event types -- the previous launch saw >= 16 events per history with 8..45 % of them scatters (big_cube, hot_zone), where
+ * event types -- work lists of >= 5e5 photons whose previous launch saw >= 16 events per history with 8..45 % of them scatters (big_cube, hot_zone), where
  * the history kernel loses a third of its lanes to divergence -- and the history kernel elsewhere; 1 = always the history
  * kernel; 2 = always the event queues.  Per-photon results do not depend on the choice (tests/test_gpu_parity.py). */
 int bgpu_set_kernel(bgpu_ctx *ctx, int choice);

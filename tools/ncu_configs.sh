@@ -12,4 +12,10 @@ for spec in "$@"; do
       > gpurun_out/ncu_${deck}_${tag}.log 2>&1
   python tools/ncu_summary.py gpurun_out/${deck}_${tag}.ncu-rep gpurun_out/${deck}_${tag}_ncu.md > /dev/null 2>&1
   cat gpurun_out/${deck}_${tag}_ncu.md
+  # per-line attribution while the report is still here, then drop it unless KEEP_REP=1 (gpurun merges <= 64 MiB back)
+  if [ -n "$LINES_KERNEL" ]; then
+    python tools/ncu_lines.py gpurun_out/${deck}_${tag}.ncu-rep branson_b200/libbranson_gpu.so "$LINES_KERNEL" 70 \
+        > gpurun_out/${deck}_${tag}_lines.txt 2>&1
+  fi
+  [ "$KEEP_REP" = 1 ] || rm -f gpurun_out/${deck}_${tag}.ncu-rep
 done
