@@ -1027,6 +1027,9 @@ int source_from_device(bgpu_ctx *c, uint32_t cycle, double dt, const double *dE_
     k_copy_soa<<<grid_for(n_cen, 256), 256, 0, c->stream>>>(c->census, 0, c->work, n_new, n_cen);
   }
   CU(c, cudaGetLastError());
+  // every photon of the work list starts as PASS (the reference's SoA setters do the same, src/source.h:27-62): a dump of
+  // the list before transport reads defined descriptors
+  if (n_total) CU(c, cudaMemsetAsync(c->d_desc, EV_PASS, n_total, c->stream));
   c->n_new = n_new;
   c->n_work = n_total;
   // pre-transport census energy, get_photon_list_E (src/replicated_driver.h:61,71)

@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
     uint32_t touched = moved | (moved >> 16);
     touched = (touched | (touched >> 8)) & 0xffu;
     masks = (masks & ~(touched * 0x01010101u)) | moved;
+    // the slots are shared by the lanes of a class from one trip to the next: order this trip's shared-memory stores
+    // before the next trip's loads (the shuffles above converge the warp but are not memory barriers)
+    __syncwarp();
   }
 
   lane_stats_flush(s_stats, LS);
