@@ -86,7 +86,8 @@ struct bgpu_ctx {
 
   // scratch (grown on demand)
   DevBuf scr_counts, scr_offsets, scr_tile_sum, scr_tile_off, scr_tiles, scr_ndep, scr_dep_off, scr_dep_cell,
-      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event, scr_tally_rep, scr_comb;
+      scr_dep_val, scr_sort, scr_keys_out, scr_vals_in, scr_vals_out, scr_seg, scr_aos, scr_event, scr_tally_rep, scr_comb,
+      scr_src_win;
   void *h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
   void *h_stage = nullptr;  // pinned staging buffers of the AoS drop-in's copy threads
@@ -895,7 +896,7 @@ void bgpu_destroy(bgpu_ctx *c) {
   DevBuf *bufs[] = {&c->scr_counts, &c->scr_offsets, &c->scr_tile_sum, &c->scr_tile_off, &c->scr_tiles, &c->scr_ndep,
                     &c->scr_dep_off, &c->scr_dep_cell, &c->scr_dep_val, &c->scr_sort, &c->scr_keys_out,
                     &c->scr_vals_in, &c->scr_vals_out, &c->scr_seg, &c->scr_aos, &c->scr_event, &c->scr_tally_rep,
-                    &c->scr_comb};
+                    &c->scr_comb, &c->scr_src_win};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   void *ptrs[] = {c->d_faces, c->d_f, c->d_opa, c->d_ops, c->d_cellrec, c->d_cell_stage, c->d_tally, c->d_stats, c->d_work_counter,
@@ -962,6 +963,19 @@ int bgpu_set_cell_groups(bgpu_ctx *c, const double *f, const double *abs_groups,
 }  // extern "C"
 
 namespace {
+// k_source_windows + k_source_sample for the S.n photons of one kind set
+int launch_source_sample(bgpu_ctx *c, SourceParams S) {
+  const uint32_t n_blocks = grid_for(S.n, SOURCE_BLOCK);
+  if (ensure(c, c->scr_src_win, 4ull * (n_blocks + 1))) return 1;
+  S.first_entry = (const uint32_t *)c->scr_src_win.p;
+  c->launches += 2;
+  k_source_windows<<<grid_for(n_blocks + 1, 256), 256, 0, c->stream>>>(S.offsets, S.n_entries, S.n, SOURCE_BLOCK, n_blocks,
+                                                                     (uint32_t *)c->scr_src_win.p);
+  k_source_sample<<<n_blocks, SOURCE_BLOCK, 0, c->stream>>>(S);
+  CU(c, cudaGetLastError());
+  return 0;
+}
+
 // make_photons / make_initial_census_photons / join_photon_arrays from per-cell energies that are already on the
 // device (ev[0] has been recorded by the caller)
 int source_from_device(bgpu_ctx *c, uint32_t cycle, double dt, const double *dE_emission, const double *dE_source,
@@ -1005,8 +1019,7 @@ int source_from_device(bgpu_ctx *c, uint32_t cycle, double dt, const double *dE_
     S.E1 = dE_source;
     // src/source.h:221-222
     S.stream_base = 10000000000000ULL * (uint64_t)cycle + c->n_user * (uint64_t)c->rank;
-    ++c->launches;
-    k_source_sample<<<grid_for(n_new, 256), 256, 0, c->stream>>>(S);
+    if (launch_source_sample(c, S)) return 1;
   }
   if (E_census) {
     if (n_init) {
@@ -1018,8 +1031,7 @@ int source_from_device(bgpu_ctx *c, uint32_t cycle, double dt, const double *dE_
       S.E0 = dE_census;
       S.E1 = nullptr;
       S.stream_base = c->n_user * (uint64_t)c->rank;  // src/source.h:144
-      ++c->launches;
-      k_source_sample<<<grid_for(n_init, 256), 256, 0, c->stream>>>(S);
+      if (launch_source_sample(c, S)) return 1;
     }
   } else if (n_cen) {
     // join_photon_arrays: all = [new ..., census ...] (src/census_functions.h:21-29)
@@ -1293,8 +1305,12 @@ int bgpu_mesh_get(bgpu_ctx *c, const char *name, double *out) {
   } else {
     return fail(c, "bgpu_mesh_get: unknown array '%s'", name);
   }
-  CU(c, cudaMemcpyAsync(out, src, 8 * nc, cudaMemcpyDeviceToHost, c->stream));
+  // through the context's pinned buffer: a copy straight into the caller's pageable array is staged by the driver in
+  // small pieces and runs at a third of the link rate
+  if (ensure_pinned(c, 8 * nc)) return 1;
+  CU(c, cudaMemcpyAsync(c->h_pinned, src, 8 * nc, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_pinned, 8 * nc);
   return 0;
 }
 

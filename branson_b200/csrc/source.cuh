@@ -6,7 +6,9 @@
 //   1. k_source_count   per cell: n = max(1, int(n_user * E_cell / total_E)) for E_cell > 0 (:230-233), the same
 //                       IEEE double expression, so counts are identical;
 //   2. exclusive scan   over the cell-major [emission, source] count pairs -> first photon index of every entry;
-//   3. k_source_sample  one thread per photon: binary search of its entry, then exactly the reference's draw order
+//   3. k_source_windows the entry of every 256th photon (one binary search per block boundary), then
+//      k_source_sample  one thread per photon: binary search of its entry inside its block's window, then exactly the
+//                       reference's draw order
 //                       get_emission_photon (:84-97) pos x,y,z -> angle (2) -> life_dx -> group = 7 draws,
 //                       get_boundary_source_photon (:100-114) face pos (2) -> cosine-law angle (2) -> life_dx -> group,
 //                       get_initial_census_photon (:117-131) pos (3) -> angle (2) -> group, life_dx = c*dt.
@@ -46,6 +48,7 @@ struct SourceParams {
   uint64_t dst_offset;   // first slot in ph to write
   uint64_t n;            // photons to make
   const uint64_t *offsets;  // exclusive scan of counts, n_entries + 1 values
+  const uint32_t *first_entry;  // k_source_windows: entry of the first photon of every SOURCE_BLOCK photons (+ the last)
   uint32_t n_entries;
   int kinds;             // 2: emission + boundary source, 1: initial census
   const double *E0, *E1;
@@ -93,37 +96,26 @@ __device__ __forceinline__ uint32_t find_entry(const uint64_t *__restrict__ offs
   return lo;
 }
 
-// The same search by a whole warp, 33-ary: every step probes 32 positions, so 1.2e6 entries take 4 dependent loads
-// instead of 20.  All 32 lanes call it with the same arguments.
-__device__ __forceinline__ uint32_t find_entry_warp(const uint64_t *__restrict__ offsets, uint32_t lo, uint32_t hi,
-                                                    uint64_t k) {
-  const uint32_t lane = threadIdx.x & 31u;
-  while (hi - lo > 1) {  // invariant: offsets[lo] <= k < offsets[hi]
-    const uint32_t step = (hi - lo + 32u) / 33u;  // >= 1
-    const uint64_t p = (uint64_t)lo + (uint64_t)step * (lane + 1u);
-    const bool le = (p < hi) && (__ldg(&offsets[p]) <= k);  // monotone over the lanes: true for the first c of them
-    const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, le));
-    const uint64_t nh = (uint64_t)lo + (uint64_t)step * (c + 1u);
-    hi = (c < 32u && nh < hi) ? (uint32_t)nh : hi;
-    lo = lo + step * c;
-  }
-  return lo;
+// entry of the first photon of every block of k_source_sample (and, in the last slot, of the last photon): a block's
+// photons are consecutive, so their entries lie inside [first[b], first[b + 1]] and every thread searches only that
+// window.  One thread per block boundary, a plain binary search over the whole table (a few microseconds in total): the
+// sampling kernel itself then needs no block-wide search and no barrier (the barrier behind the in-kernel window search
+// was 32 % of its stall samples, profiles/source_r02_v18_ncu.md).
+__global__ void k_source_windows(const uint64_t *__restrict__ offsets, uint32_t n_entries, uint64_t n, uint32_t block,
+                                 uint32_t n_blocks, uint32_t *__restrict__ first) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_blocks) return;
+  uint64_t k = (uint64_t)b * block;
+  if (k > n - 1) k = n - 1;
+  first[b] = find_entry(offsets, 0, n_entries, k);
 }
 
-__global__ void __launch_bounds__(256) k_source_sample(const SourceParams P) {
-  // The block's photons are consecutive, so their entries lie between the entry of its first and of its last photon:
-  // two warps search the whole table for those two, everyone else only that window.
-  __shared__ uint32_t s_win[2];
-  const uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x;
-  const uint64_t k = k0 + threadIdx.x;
-  if (threadIdx.x < 64) {
-    const uint64_t kl = (k0 + blockDim.x - 1 < P.n) ? k0 + blockDim.x - 1 : P.n - 1;
-    const uint32_t e = find_entry_warp(P.offsets, 0, P.n_entries, (threadIdx.x < 32) ? k0 : kl);
-    if ((threadIdx.x & 31u) == 0) s_win[threadIdx.x >> 5] = e;
-  }
-  __syncthreads();
+constexpr int SOURCE_BLOCK = 256;
+
+__global__ void __launch_bounds__(SOURCE_BLOCK) k_source_sample(const SourceParams P) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P.n) return;
-  const uint32_t lo = find_entry(P.offsets, s_win[0], s_win[1] + 1, k);
+  const uint32_t lo = find_entry(P.offsets, __ldg(&P.first_entry[blockIdx.x]), __ldg(&P.first_entry[blockIdx.x + 1]) + 1, k);
   const uint32_t entry = lo;
   const uint32_t cell = (P.kinds == 2) ? (entry >> 1) : entry;
   const bool boundary_source = (P.kinds == 2) && (entry & 1u);
