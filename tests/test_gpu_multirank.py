@@ -92,9 +92,10 @@ def test_in_process_ranks_match_n_rank_oracle(name, make, n_ranks, mesh, tmp_pat
         d.close()
 
 
-def test_cli_ranks_share_one_gpu(tmp_path):
-    """bin/branson --ranks 2: the reference's `mpirun -n 2 BRANSON deck.xml` in one process (in-process collectives on a
-    one-GPU box); its printed conservation lines equal the 2-rank oracle's"""
+def test_cli_two_ranks_in_one_process(tmp_path):
+    """bin/branson --ranks 2: the reference's `mpirun -n 2 BRANSON deck.xml` in one process, one host thread per rank
+    (rank r on GPU r % n_devices: in-process collectives on a one-GPU box, ncclCommInitAll + NCCL on a box with two); its
+    printed photon counts equal the 2-rank oracle's"""
     from oracle import port
     deck = decks.hohlraum_multi(photons=40000, t_stop=0.003, scale=5).with_(dd_transport_type="REPLICATED")
     xml = deck.write(str(tmp_path / "deck.xml"))
