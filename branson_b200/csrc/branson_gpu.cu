@@ -40,7 +40,7 @@ struct DevBuf {
 
 }  // namespace
 
-constexpr int WORK_COUNTERS = 16;  // [0]: every ordinary launch; [j]: slice j of the pipelined AoS drop-in
+constexpr int WORK_COUNTERS = 64;  // [0]: every ordinary launch; [j]: slice j of the pipelined AoS drop-in
 
 struct bgpu_ctx {
   int device = 0;
@@ -1628,9 +1628,14 @@ int transport_aos_pipelined(bgpu_ctx *c, uint8_t *photons, uint64_t n, uint64_t 
     CU(c, cudaHostAlloc(&c->h_stage, stage_bytes, cudaHostAllocDefault));
     c->h_stage_bytes = stage_bytes;
   }
-  // slices of at least 2^19 photons (enough to fill the persistent grid several times over), at most WORK_COUNTERS of
+  // slices of at least 2^20 photons (enough to fill the persistent grid several times over), at most WORK_COUNTERS of
   // them, whole chunks each
-  uint64_t m = std::max<uint64_t>(1ull << 19, (n + WORK_COUNTERS - 1) / WORK_COUNTERS);
+  // (slice size swept on the bench workload, 1.05e7 photons, one box: 2^16 111 ms, 2^17 99, 2^18 90, 2^19 81, 2^20 78 --
+  // every slice is a launch of the persistent grid with its own tail of long histories, which costs more than the
+  // longer fill and drain of big slices; BRANSON_AOS_SLICE overrides)
+  uint64_t min_slice = 1ull << 20;
+  if (const char *e = getenv("BRANSON_AOS_SLICE")) { const long long v = atoll(e); if (v >= (1ll << 16)) min_slice = (uint64_t)v; }
+  uint64_t m = std::max<uint64_t>(min_slice, (n + WORK_COUNTERS - 1) / WORK_COUNTERS);
   m = (m + AOS_CHUNK - 1) / AOS_CHUNK * AOS_CHUNK;
   const uint32_t n_slices = (uint32_t)((n + m - 1) / m);
   const uint64_t chunks_per_slice = m / AOS_CHUNK;
