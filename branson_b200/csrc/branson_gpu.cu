@@ -1397,8 +1397,8 @@ int comm_allreduce_device(bgpu_ctx *c, double *ptr, uint64_t n, int op /* ncclRe
     const ncclResult_t r = api.AllReduce(ptr, ptr, n, ncclDouble, (ncclRedOp_t)op, c->comm.nccl, c->stream);
     if (r != ncclSuccess) return fail(c, "ncclAllReduce: %s", api.GetErrorString(r));
   } else if (c->comm.kind == COMM_LOCAL) {
-    const char *e = local_allreduce(*c->comm.local, c->rank, ptr, n, op, c->stream);
-    if (e) return fail(c, "in-process all-reduce: %s", e);
+    const std::string e = local_allreduce(*c->comm.local, c->rank, ptr, n, op, c->stream);
+    if (!e.empty()) return fail(c, "in-process all-reduce: %s", e.c_str());
   } else {
     return fail(c, "rank %d of %d has no communicator (bgpu_comm_init_rank / bgpu_comm_init_local)", c->rank, c->n_ranks);
   }

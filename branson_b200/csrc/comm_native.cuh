@@ -144,9 +144,9 @@ struct CommHandle {
   }
 };
 
-// in-place sum of n doubles at `ptr` (device memory of this rank) over the group, ordered on `stream`; returns an
-// error text or nullptr
-inline const char *local_allreduce(LocalGroup &g, int rank, double *ptr, uint64_t n, int op, cudaStream_t stream) {
+// in-place reduction of n doubles at `ptr` (device memory of this rank) over the group, ordered on `stream`; returns an
+// error text, empty on success (a copy: the group's own message may be rewritten by the next collective)
+inline std::string local_allreduce(LocalGroup &g, int rank, double *ptr, uint64_t n, int op, cudaStream_t stream) {
   cudaError_t e = cudaEventRecord(g.ev_ready[rank], stream);
   if (e != cudaSuccess) return cudaGetErrorString(e);
   {
@@ -155,7 +155,7 @@ inline const char *local_allreduce(LocalGroup &g, int rank, double *ptr, uint64_
     g.count[rank] = n;
     const uint64_t gen = g.generation;
     if (++g.arrived == g.n_ranks) {
-      // the last rank to arrive sums on its own stream, behind every rank's pending work
+      // the last rank to arrive reduces on its own stream, behind every rank's pending work
       g.status = cudaSuccess;
       g.error.clear();
       for (int r = 0; r < g.n_ranks && g.status == cudaSuccess; ++r) {
@@ -174,16 +174,17 @@ inline const char *local_allreduce(LocalGroup &g, int rank, double *ptr, uint64_
         g.status = cudaGetLastError();
       }
       if (g.status == cudaSuccess) g.status = cudaEventRecord(g.ev_done, stream);
+      if (g.status != cudaSuccess && g.error.empty()) g.error = cudaGetErrorString(g.status);
       g.arrived = 0;
       ++g.generation;
       g.cv.notify_all();
     } else {
       g.cv.wait(lk, [&] { return g.generation != gen; });
     }
-    if (g.status != cudaSuccess) return g.error.empty() ? cudaGetErrorString(g.status) : g.error.c_str();
+    if (g.status != cudaSuccess) return g.error;
   }
   e = cudaStreamWaitEvent(stream, g.ev_done, 0);
-  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+  return e == cudaSuccess ? std::string() : std::string(cudaGetErrorString(e));
 }
 
 }  // namespace bg

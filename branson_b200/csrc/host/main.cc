@@ -97,7 +97,6 @@ int main(int argc, char **argv) {
     }
     const double t0 = wall_now();
     std::mutex err_mutex;
-    std::string first_error;
     auto run = [&](int r) {
       try {
         Rank &rk = *ranks[(size_t)r];
