@@ -497,6 +497,9 @@ int run_event(bgpu_ctx *c, TransportParams P) {
   return 0;
 }
 
+// the slot record of the queue kernel holds i and j in 16 bits each and k in 24 (pool.cuh, PV_SK)
+bool pool_mesh_ok(const bgpu_ctx *c) { return c->mesh.nx < 65536u && c->mesh.ny < 65536u && c->mesh.nz < (1u << 24); }
+
 // BGPU_EVENT, default form: event queues in shared memory (pool.cuh); tallies and statistics as in the history launch
 int launch_pool(bgpu_ctx *c, const TransportParams &P) {
   const size_t face_bytes = (size_t)P.mesh.n_faces * 8;
@@ -612,8 +615,10 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
   c->kernel_used = 0u;
   if (algorithm == BGPU_EVENT) {
     if (tally_mode != BGPU_TALLY_ATOMIC) return fail(c, "the event-based variant supports BGPU_TALLY_ATOMIC only");
-    c->kernel_used = c->event_hbm ? 2u : 1u;
-    if (c->event_hbm) return run_event(c, P);
+    // (the queue kernel packs a slot's i | j << 16 and k | descriptor << 24: meshes beyond that take the HBM-pass form)
+    const bool hbm = c->event_hbm || !pool_mesh_ok(c);
+    c->kernel_used = hbm ? 2u : 1u;
+    if (hbm) return run_event(c, P);
     CU(c, cudaMemsetAsync(c->d_work_counter, 0, 8, c->stream));
     if (prepare_tally_copies(c)) return 1;
     const uint32_t copies = c->tally_copies_live;
@@ -645,7 +650,7 @@ int run_transport(bgpu_ctx *c, int algorithm, int tally_mode, bool writeback_all
     // the resident slots a few times is left to the history kernel)
     const bool mixed = c->prev_events_per_history >= 16.0 && c->prev_scatter_fraction >= 0.08 &&
                        c->prev_scatter_fraction <= 0.45 && c->n_work >= 500000ull;
-    const bool queues = c->kernel_choice == 2 || (c->kernel_choice == 0 && mixed);
+    const bool queues = pool_mesh_ok(c) && (c->kernel_choice == 2 || (c->kernel_choice == 0 && mixed));
     c->kernel_used = queues ? 1u : 0u;
     if (queues ? launch_pool(c, P) : launch_history<TM_ATOMIC>(c, P)) return 1;
     if (copies > 1) {
