@@ -374,6 +374,8 @@ def run_extra_config(name, deck, cycles, world, rank, local, dist):
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         total = r["pre_census_E"] + r["emission_E"] + r["source_E"]
         rows.append({"cycle": c + 1, "histories": int(r["trans_particles"]), "ms_transport_max": v[0].item(),
+                     "algorithmic_GBs_rank0": algorithmic_bytes(g) / max(1e-9, g["ms_transport"] * 1e-3) / 1e9,
+                     "kernel_rank0": {0: "history", 1: "queues", 2: "passes"}.get(g.get("transport_kernel", 0), "?"),
                      "ms_cycle_wall_max": v[1].item(), "ms_source_max": v[2].item(), "ms_census_max": v[3].item(),
                      "events_per_history_rank0": g["n_events"] / max(1, g["n_transported"]),
                      "rad_balance_rel": abs(r["rad_balance_exact"]) / max(1e-300, total)})
@@ -390,6 +392,10 @@ def run_extra_config(name, deck, cycles, world, rank, local, dist):
             "ms_transport_per_cycle": sum(x["ms_transport_max"] for x in q) / len(q),
             "ms_whole_cycle": sum(x["ms_cycle_wall_max"] for x in q) / len(q),
             "collectives_per_cycle": info["calls"] / cycles, "max_rad_balance_rel": max(x["rad_balance_rel"] for x in rows),
+            "roofline_rank0": {"bound": "hbm", "achieved": sum(x["algorithmic_GBs_rank0"] for x in q) / len(q),
+                               "peak": measured_peak()[0], "unit": "GB/s",
+                               "frac": sum(x["algorithmic_GBs_rank0"] for x in q) / len(q) / measured_peak()[0],
+                               "kernel": q[-1]["kernel_rank0"]},
             "unit": UNIT, "cycles": rows}
 
 
