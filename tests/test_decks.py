@@ -66,3 +66,21 @@ def test_fixture_is_current_against_the_reference_tree():
     for name, (g, force) in gen.DECKS.items():
         assert gen.fingerprint(os.path.join(gen.REF_INPUTS, name), g, force) == GOLDEN[name], name
     assert gen.big_cube_text_fingerprint(os.path.join(gen.REF_INPUTS, "big_cube.xml")) == GOLDEN["big_cube.xml"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="/root/reference is not present on this machine")
+def test_dropin_patch_applies_to_the_reference_tree(tmp_path):
+    """oracle/dropin.patch (INTEGRATION.md level 1) must apply cleanly to the four reference headers it names"""
+    import shutil
+    import subprocess
+    names = ["gpu_setup.h", "history_based_transport.h", "replicated_transport.h", "replicated_driver.h"]
+    for n in names:
+        shutil.copy(os.path.join("/root/reference/src", n), tmp_path / n)
+    r = subprocess.run(["patch", "-s", "-d", str(tmp_path), "-p1", "-i", os.path.join(ROOT, "oracle", "dropin.patch")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    patched = "".join(open(tmp_path / n).read() for n in names)
+    assert "bgpu_transport_photons_aos" in patched and "BRANSON_B200" in patched
+    # everything the patch adds is guarded: without -DBRANSON_B200 the headers are the reference's own
+    for n in names:
+        assert not list(tmp_path.glob(n + ".rej"))
