@@ -783,17 +783,27 @@ int run_census(bgpu_ctx *c, double next_dt, bool serial_sums) {
   return 0;
 }
 
-int list_energy(bgpu_ctx *c, const PhotonSoA &list, uint64_t off, uint64_t n, double *out, int use_E0 = 0) {
-  *out = 0.0;
-  if (!n) return 0;
+// sum of E (or E0) over a photon list into d_results[slot], stream-ordered (no host synchronisation)
+int list_energy_async(bgpu_ctx *c, const PhotonSoA &list, uint64_t off, uint64_t n, int slot, int use_E0 = 0) {
+  if (!n) {
+    CU(c, cudaMemsetAsync(c->d_results + slot, 0, 8, c->stream));
+    return 0;
+  }
   const uint32_t tiles = (uint32_t)((n + CT_TILE - 1) / CT_TILE);
   if (ensure(c, c->scr_tile_sum, 8ull * tiles + 8)) return 1;
   double *tile_E = (double *)c->scr_tile_sum.p;
   ++c->launches;
   k_list_E_tiles<<<tiles, CT_THREADS, 0, c->stream>>>(list.ee + off, n, tile_E, use_E0);
   ++c->launches;
-  k_sum_ordered<<<1, 1024, 0, c->stream>>>(tile_E, tiles, c->d_results + 2);
+  k_sum_ordered<<<1, 1024, 0, c->stream>>>(tile_E, tiles, c->d_results + slot);
   CU(c, cudaGetLastError());
+  return 0;
+}
+
+int list_energy(bgpu_ctx *c, const PhotonSoA &list, uint64_t off, uint64_t n, double *out, int use_E0 = 0) {
+  *out = 0.0;
+  if (!n) return 0;
+  if (list_energy_async(c, list, off, n, 2, use_E0)) return 1;
   CU(c, cudaMemcpyAsync(out, c->d_results + 2, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -1060,10 +1070,15 @@ int source_from_device(bgpu_ctx *c, uint32_t cycle, double dt, const double *dE_
   c->n_new = n_new;
   c->n_work = n_total;
   // pre-transport census energy, get_photon_list_E (src/replicated_driver.h:61,71)
-  if (list_energy(c, c->work, n_new, n_cen, &c->pre_census_E)) return 1;
-  if (list_energy(c, c->work, 0, n_new, &c->new_photon_E, 1)) return 1;
+  // (the second reduction reuses the tile scratch of the first: both are ordered on the ctx stream)
+  if (list_energy_async(c, c->work, n_new, n_cen, 2)) return 1;
+  if (list_energy_async(c, c->work, 0, n_new, 3, 1)) return 1;
+  double h_E[2] = {0.0, 0.0};
+  CU(c, cudaMemcpyAsync(h_E, c->d_results + 2, 16, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaEventRecord(c->ev[1], c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  c->pre_census_E = h_E[0];
+  c->new_photon_E = h_E[1];
   c->stats = bgpu_cycle_stats{};
   c->stats.pre_census_E = c->pre_census_E;
   c->stats.new_photon_E = c->new_photon_E;
@@ -1140,7 +1155,7 @@ void unpack_sums(const double *h, uint32_t q_mask, bgpu_mesh_sums *out) {
 // the tile sums -> d_mesh_sums[block][q] for `n_blocks` rank blocks (no host synchronisation)
 int mesh_final_sums_async(bgpu_ctx *c, uint32_t q_mask, uint32_t n_blocks) {
   ++c->launches;
-  k_mesh_final_sums<<<n_blocks, 32, 0, c->stream>>>(c->d_tile_sums, c->mesh_tiles, q_mask, c->d_mesh_sums);
+  k_mesh_final_sums<<<n_blocks, 256, 0, c->stream>>>(c->d_tile_sums, c->mesh_tiles, q_mask, c->d_mesh_sums);
   CU(c, cudaGetLastError());
   return 0;
 }

@@ -265,16 +265,29 @@ __global__ void __launch_bounds__(MESH_TILE_THREADS) k_mesh_update_temperature(c
   tile_store(s_mat, s_red, &P.tile_sums[MS_POST_MAT * nt + blockIdx.x]);
 }
 
-// the tiles in order, one thread per quantity and rank block: out[r][q] = sum_t tile_sums[r][q][t]
-// (blockIdx.x = r; the kernels that are not per-rank use block 0 = the rank's own block)
-__global__ void k_mesh_final_sums(const double *__restrict__ tile_sums, uint32_t n_tiles, uint32_t q_mask,
-                                  double *__restrict__ out) {
-  const uint32_t q = threadIdx.x;
-  if (q >= MS_N || !((q_mask >> q) & 1u)) return;
-  const double *v = tile_sums + ((uint64_t)blockIdx.x * MS_N + q) * n_tiles;
-  double s = 0.0;
-  for (uint32_t t = 0; t < n_tiles; ++t) s += v[t];
-  out[blockIdx.x * MS_N + q] = s;
+// out[r][q] = sum_t tile_sums[r][q][t] in a fixed order: blockIdx.x = r (the kernels that are not per-rank use block 0 =
+// the rank's own block); for every requested quantity thread t adds its contiguous run of tiles serially and the 256 runs
+// are added by a fixed tree -- reproducible, identical on every rank, a few microseconds for the 7 813 tiles of the 200^3
+// cube where one thread per quantity took 35
+__global__ void __launch_bounds__(256) k_mesh_final_sums(const double *__restrict__ tile_sums, uint32_t n_tiles,
+                                                         uint32_t q_mask, double *__restrict__ out) {
+  __shared__ double s[256];
+  const uint32_t per = (n_tiles + 255u) / 256u;
+  const uint32_t b = threadIdx.x * per, e = (b + per < n_tiles) ? b + per : n_tiles;
+  for (uint32_t q = 0; q < (uint32_t)MS_N; ++q) {
+    if (!((q_mask >> q) & 1u)) continue;  // (uniform over the block)
+    const double *v = tile_sums + ((uint64_t)blockIdx.x * MS_N + q) * n_tiles;
+    double acc = 0.0;
+    for (uint32_t i = b; i < e; ++i) acc += v[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t w = 128; w > 0; w >>= 1) {
+      if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x * MS_N + q] = s[0];
+    __syncthreads();
+  }
 }
 
 }  // namespace bg
