@@ -38,6 +38,9 @@ namespace bg {
 #define POOL_MIN_BLOCKS 5
 #endif
 #define POOL_ROWS 2  // (work-list photons per resident thread the launcher assumes when it trims the grid)
+#ifndef POOL_STICKY_LANES
+#define POOL_STICKY_LANES 28u  // an advance block re-runs without an election while it serves at least this many lanes
+#endif
 
 // slot states = byte index of the class's mask register
 enum : uint32_t { PM_ADV = 0u, PM_SCAT = 1u, PM_DONE = 2u, PM_EMPTY = 3u };
@@ -116,8 +119,14 @@ template <bool COUNTERS, bool SMEM, bool PACKED>
 __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const PoolParams Q) {
   extern __shared__ __align__(16) char s_dyn[];  // [pool: 4 warps][faces]
   __shared__ uint32_t s_stats[12];
+  __shared__ uint8_t s_nth[(1 << POOL_K) * 4];
   const TransportParams &P = Q.T;
   if (threadIdx.x < 12) s_stats[threadIdx.x] = 0u;
+  for (uint32_t e = threadIdx.x; e < (4u << POOL_K); e += blockDim.x) {  // s_nth[m][r] = index of the r-th set bit of m (0 if none)
+    uint32_t m = e >> 2;
+    for (uint32_t i = 0; i < (e & 3u); ++i) m &= m - 1u;
+    s_nth[e] = (uint8_t)(m ? __ffs((int)m) - 1 : 0);
+  }
   double *s_faces = reinterpret_cast<double *>(s_dyn + 4 * POOL_BYTES_PER_WARP);
   const double *faces;
   if (SMEM) {
@@ -146,13 +155,10 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
   const uint32_t cls = lane_id & 7u, rank = lane_id >> 3;
   char *const cls_pool = s_dyn + warp_id * POOL_BYTES_PER_WARP + cls * 16;
   auto slot_of = [&](int j) { return PoolSlot{cls_pool + (size_t)j * 128}; };  // slot s = 8 j + cls: byte offset 16 s
-  // the j of the class's rank-th slot whose bit is set in the 8-bit mask m, or -1
-  auto pick = [&](uint32_t m) {
-    m &= 0xffu;
-#pragma unroll
-    for (uint32_t i = 0; i < 3; ++i) m = (i < rank) ? (m & (m - 1u)) : m;
-    return m ? (int)__ffs((int)m) - 1 : -1;
-  };
+  // the j of the class's rank-th slot whose bit is set in the 8-bit mask m (the caller knows there is one): a 512-byte
+  // table in shared memory, [mask][rank] -> bit index, filled once per CTA
+  const uint8_t *const my_nth = s_nth + rank;
+  auto pick = [&](uint32_t m) { return (int)my_nth[(m & 0xffu) * 4u]; };
 
   double2 *my_tally = P.tally;
   if (P.tally_copies > 1u) {
@@ -173,19 +179,33 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
   LaneStats LS{0u, 0u, 0u, 0u, 0u};
   const uint32_t T_S = Q.batch_scatter, T_R = Q.batch_refill;
 
+  bool last_was_A = false;
   for (;;) {
-    const uint32_t mA = masks >> (8 * PM_ADV), mS = masks >> (8 * PM_SCAT);
-    const uint32_t mR = (masks >> (8 * PM_DONE)) | (exhausted ? 0u : (masks >> (8 * PM_EMPTY)));
-    const bool hasA = rank < (uint32_t)__popc(mA & 0xffu), hasS = rank < (uint32_t)__popc(mS & 0xffu);
-    const bool hasR = rank < (uint32_t)__popc(mR & 0xffu);
-    const unsigned bA = __ballot_sync(FULL, hasA), bS = __ballot_sync(FULL, hasS), bR = __ballot_sync(FULL, hasR);
-    if ((bA | bS | bR) == 0u) break;
-    const uint32_t nA = __popc(bA), nS = __popc(bS), nR = __popc(bR);
-    // the election: the block that serves the most lanes, with a head start for A (the common event)
-    int block;  // 0 A, 1 S, 2 R
-    if (nR && (nR >= T_R || (nR >= nA && nR >= nS))) block = 2;
-    else if (nS && (nS >= T_S || nS >= nA)) block = 1;
-    else block = 0;
+    const uint32_t mA = masks >> (8 * PM_ADV);
+    const bool hasA = rank < (uint32_t)__popc(mA & 0xffu);
+    const unsigned bA = __ballot_sync(FULL, hasA);
+    const uint32_t nA = __popc(bA);
+    uint32_t mS = 0u;
+    bool hasS = false, hasR = false;
+    unsigned bS = 0u;
+    int block = 0;  // 0 A, 1 S, 2 R
+    // An advance block that still fills the warp follows the previous one without an election (the other two counts
+    // are not even formed); the scatters and finished records it leaves waiting are served, by more lanes at once,
+    // as soon as it does not.
+    if (!(last_was_A && nA >= POOL_STICKY_LANES)) {
+      mS = masks >> (8 * PM_SCAT);
+      const uint32_t mR = (masks >> (8 * PM_DONE)) | (exhausted ? 0u : (masks >> (8 * PM_EMPTY)));
+      hasS = rank < (uint32_t)__popc(mS & 0xffu);
+      hasR = rank < (uint32_t)__popc(mR & 0xffu);
+      bS = __ballot_sync(FULL, hasS);
+      const unsigned bR = __ballot_sync(FULL, hasR);
+      if ((bA | bS | bR) == 0u) break;
+      const uint32_t nS = __popc(bS), nR = __popc(bR);
+      // the election: the block that serves the most lanes, with a head start for A (the common event)
+      if (nR && (nR >= T_R || (nR >= nA && nR >= nS))) block = 2;
+      else if (nS && (nS >= T_S || nS >= nA)) block = 1;
+    }
+    last_was_A = block == 0;
     uint32_t moved = 0u;  // this lane's slot in its new state's byte (the class ORs these together below)
 
     if (block == 0) {
@@ -258,11 +278,8 @@ __global__ void __launch_bounds__(128, POOL_MIN_BLOCKS) k_transport_pool(const P
         if (rank < nD) {
           j = pick(mD);
           retire = true;
-        } else {
-          uint32_t m = (masks >> (8 * PM_EMPTY)) & 0xffu;
-#pragma unroll
-          for (uint32_t i = 0; i < 3; ++i) m = (i + nD < rank) ? (m & (m - 1u)) : m;
-          j = m ? (int)__ffs((int)m) - 1 : -1;
+        } else {  // (hasR: the class has more than rank - nD empty slots)
+          j = (int)s_nth[((masks >> (8 * PM_EMPTY)) & 0xffu) * 4u + (rank - nD)];
         }
       }
       const PoolSlot sl = slot_of(j < 0 ? 0 : j);
