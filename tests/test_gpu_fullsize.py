@@ -98,6 +98,44 @@ def test_big_cube_photons_match_reference_at_2e7(tmp_path):
     _photons_against_reference(decks.big_cube(n=200, photons=20_000_000, t_stop=0.002), 2, tmp_path)
 
 
+@pytest.mark.parametrize("make", [lambda: decks.hot_zone(photons=10_000_000, t_stop=0.03),
+                                  lambda: decks.hohlraum_single(photons=3_000_000, t_stop=0.03)], ids=["hot_zone_1e7", "hohlraum_3e6"])
+def test_kernel_choice_is_invisible_at_size(make, tmp_path):
+    """BGPU_HISTORY served by the history kernel and by the event-queue kernel (csrc/pool.cuh) runs the same device
+    functions per photon in the same order: every photon's final record -- integers AND doubles -- must be bit-identical
+    between the two in the first cycle, the integers in every cycle (only the order of the atomic tally sums differs)."""
+    deck = make()
+    outs = []
+    for kernel in (gpu.KERNEL_HISTORY, gpu.KERNEL_QUEUES):
+        d = driver.Driver(deck.write(str(tmp_path / f"{deck.name}_{kernel}.xml")), n_groups=deck.n_groups, device=0,
+                          validate=True, mesh_on_device=True)
+        view = d.gpu_context()
+        view.set_kernel(kernel)
+        cyc = []
+        for _ in range(3):
+            rep = d.cycle()
+            post = view.download(gpu.LIST_WORK, counters=True)
+            cyc.append((rep, post, d.array("abs_E")))
+            assert rep["gpu"]["transport_kernel"] == (1 if kernel == gpu.KERNEL_QUEUES else 0)
+        outs.append(cyc)
+        d.close()
+    for (rh, ph, ah), (rq, pq, aq) in zip(*outs):
+        for k in ("cell", "group", "ctr", "descriptor", "counters"):
+            assert np.array_equal(ph[k], pq[k]), (rh["step"], k)
+        for k in ("E", "pos", "angle", "life_dx"):
+            if rh["step"] == 1:
+                # same inputs, same per-photon arithmetic: bit for bit
+                assert np.array_equal(ph[k].view(np.uint64), pq[k].view(np.uint64)), (rh["step"], k)
+            else:
+                # (from the second cycle on the two runs start from temperatures that differ in their last bits: the
+                # atomic tallies of cycle 1 were summed in different orders)
+                assert np.max(np.abs(ph[k] - pq[k])) <= 1e-9 * max(np.max(np.abs(ph[k])), 1e-300), (rh["step"], k)
+        for k in ("n_events", "n_scatters", "n_crossings", "n_reflections", "n_census", "n_killed", "n_exit",
+                  "n_group_lookups", "n_deposits"):
+            assert rh["gpu"][k] == rq["gpu"][k], (rh["step"], k)
+        assert np.max(np.abs(ah - aq)) <= 1e-12 * np.max(np.abs(ah))
+
+
 def test_hohlraum_single_node_full_size(tmp_path):
     # configs[2]: 65 x 65 x 140 cells, 30 groups, 1e7 photons (reference inputs/3D_hohlraum_single_node.xml)
     deck = decks.hohlraum_single(t_stop=0.02)
