@@ -108,7 +108,8 @@ struct bgpu_ctx {
   uint32_t event_passes = 0;
   // BGPU_EVENT: 0 = event queues in shared memory (pool.cuh, default), 1 = lockstep passes through HBM (event.cuh)
   int event_hbm = 0;
-  uint32_t pool_batch_scatter = 24, pool_batch_refill = 16;
+  // (swept with the v21 kernel, profiles/pool_thresholds_r02.txt: 20 / 8 is 2 % ahead of the first version's 24 / 16)
+  uint32_t pool_batch_scatter = 20, pool_batch_refill = 8;
   // BGPU_HISTORY: which kernel runs the histories (per-photon results are identical): 0 = auto -- the event-queue kernel
   // on decks that MIX event types (previous launch: >= 16 events per history, 8..45 % of them scatters: big_cube,
   // hot_zone), the history kernel elsewhere; 1 = always the history kernel; 2 = always the event queues

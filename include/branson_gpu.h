@@ -238,7 +238,7 @@ int bgpu_set_kernel(bgpu_ctx *ctx, int choice);
  * two photon slots, each trip the warp elects the event type most lanes can serve (advance / scatter / retire+refill)
  * and runs that block alone: the regrouping of the reference's event_based_transport.h at warp scope, without HBM
  * traffic.  batch_scatter / batch_refill = lanes that must hold a parked scatter / a finished or empty slot before that
- * block is elected over a fuller advance block (0 = keep; defaults 24 / 16).  hbm_passes = 1: the first form, lockstep
+ * block is elected over a fuller advance block (0 = keep; defaults 20 / 8).  hbm_passes = 1: the first form, lockstep
  * passes over active lists in HBM (csrc/event.cuh; bgpu_set_event_tail applies to it); < 0 keeps the current form. */
 int bgpu_set_event_mode(bgpu_ctx *ctx, int hbm_passes, int batch_scatter, int batch_refill);
 /* sample_emission_group (src/sampling_functions.h:126-138): 1 (default) = when every cell's groups are equal, use the
